@@ -1,0 +1,82 @@
+// Host-side helpers shared by all launchers: error checks, TMA tensor-map
+// encoding (driver entry point resolved at runtime, so the library never links
+// libcuda directly and can be built on a GPU-less box), device properties.
+#pragma once
+
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+
+#define GLLM_EXPORT extern "C" __attribute__((visibility("default")))
+
+#define CUDA_CHECK_RET(expr)                                                              \
+  do {                                                                                    \
+    cudaError_t _e = (expr);                                                              \
+    if (_e != cudaSuccess) {                                                              \
+      fprintf(stderr, "[gllm_b200] CUDA error %s at %s:%d: %s\n", #expr, __FILE__, __LINE__, \
+              cudaGetErrorString(_e));                                                    \
+      return static_cast<int>(_e);                                                        \
+    }                                                                                     \
+  } while (0)
+
+namespace b200 {
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                    const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                    const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+inline PFN_encodeTiled get_encode_fn() {
+  static PFN_encodeTiled fn = nullptr;
+  if (fn == nullptr) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q);
+    if (e != cudaSuccess || p == nullptr) {
+      fprintf(stderr, "[gllm_b200] cannot resolve cuTensorMapEncodeTiled (%s)\n",
+              cudaGetErrorString(e));
+      abort();
+    }
+    fn = reinterpret_cast<PFN_encodeTiled>(p);
+  }
+  return fn;
+}
+
+// 2-D row-major tensor [rows, cols] of `elem_bytes`-sized elements with row pitch
+// `ld_bytes`; box = [box_rows, box_cols]; 128-byte swizzle (box_cols*elem_bytes == 128)
+// unless `swizzle128` is false.
+inline int make_tmap_2d(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols,
+                        uint64_t ld_bytes, uint32_t box_rows, uint32_t box_cols,
+                        CUtensorMapDataType dtype, bool swizzle128 = true) {
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {ld_bytes};
+  cuuint32_t box[2] = {box_cols, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = get_encode_fn()(
+      map, dtype, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+      swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+      CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    fprintf(stderr,
+            "[gllm_b200] cuTensorMapEncodeTiled failed (%d): base=%p rows=%llu cols=%llu ld=%llu "
+            "box=%ux%u\n",
+            (int)r, base, (unsigned long long)rows, (unsigned long long)cols,
+            (unsigned long long)ld_bytes, box_rows, box_cols);
+    return 1;
+  }
+  return 0;
+}
+
+inline int num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+  }
+  return n;
+}
+
+}  // namespace b200

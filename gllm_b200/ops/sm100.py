@@ -1,0 +1,277 @@
+"""Python front-ends of the hand-written sm_100a kernels (ctypes -> libgllm_b200.so).
+
+Each function validates shapes/dtypes, allocates the output and launches on the current
+CUDA stream. No fallback: if the library is missing on a GPU box this raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from typing import Optional
+
+import torch
+
+from gllm_b200.ops import lib as _lib
+from gllm_b200.ops.lib import GemmComm, check, stream_ptr
+
+_BF16 = torch.bfloat16
+NUM_SMS = 148
+
+
+def _p(t: Optional[torch.Tensor]):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+_launch_count = 0
+
+
+def launches() -> int:
+    """Number of kernel launches issued through this module (bench.py `gpu_launches`)."""
+    return _launch_count
+
+
+def _count(n=1):
+    global _launch_count
+    _launch_count += n
+
+
+# ----------------------------------------------------------------------------------------------
+# GEMM
+# ----------------------------------------------------------------------------------------------
+_FORCE_BN = int(os.environ.get("GLLM_GEMM_BN", "0"))
+
+
+def linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None,
+           out: Optional[torch.Tensor] = None, comm: Optional[GemmComm] = None, epi: int = 0) -> torch.Tensor:
+    """y = x @ w.T (+ bias). x [M, K] (row stride arbitrary, unit inner stride), w [N, K]."""
+    assert x.dtype == _BF16 and w.dtype == _BF16, (x.dtype, w.dtype)
+    assert x.dim() == 2 and w.dim() == 2 and x.shape[1] == w.shape[1], (x.shape, w.shape)
+    assert x.stride(1) == 1 and w.stride(1) == 1
+    m, k = x.shape
+    n = w.shape[0]
+    n_out = n // 2 if epi == 1 else n
+    if out is None:
+        out = torch.empty(m, n_out, dtype=_BF16, device=x.device)
+    else:
+        assert out.shape == (m, n_out) and out.stride(1) == 1
+    if m == 0:
+        return out
+    L = _lib.load()
+    rc = L.gllm_gemm_bf16(_p(x), x.stride(0), _p(w), w.stride(0), _p(out), out.stride(0), m, n, k, _p(bias),
+                          epi, _FORCE_BN, ctypes.byref(comm) if comm is not None else None, stream_ptr())
+    check(rc, "gemm_bf16")
+    _count()
+    return out
+
+
+def linear_silu_mul(x: torch.Tensor, w_interleaved: torch.Tensor, out: Optional[torch.Tensor] = None):
+    """Fused gate/up projection + SiLU-gate epilogue; weight rows interleaved per 64
+    (see ops.ref.interleave_gate_up)."""
+    # kernels with BN=128 interleave at 64 rows: force BN=128 so tile == [64 gate | 64 up]
+    assert x.dtype == _BF16 and w_interleaved.dtype == _BF16
+    m, k = x.shape
+    n = w_interleaved.shape[0]
+    if out is None:
+        out = torch.empty(m, n // 2, dtype=_BF16, device=x.device)
+    if m == 0:
+        return out
+    L = _lib.load()
+    rc = L.gllm_gemm_bf16(_p(x), x.stride(0), _p(w_interleaved), w_interleaved.stride(0), _p(out),
+                          out.stride(0), m, n, k, None, 1, 128, None, stream_ptr())
+    check(rc, "gemm_bf16(silu)")
+    _count()
+    return out
+
+
+# ----------------------------------------------------------------------------------------------
+# norm / activation / embedding
+# ----------------------------------------------------------------------------------------------
+def rmsnorm(x: torch.Tensor, w: torch.Tensor, eps: float, residual: Optional[torch.Tensor] = None,
+            out: Optional[torch.Tensor] = None, residual_out: Optional[torch.Tensor] = None):
+    assert x.dtype == _BF16 and x.dim() == 2 and x.stride(1) == 1
+    t, h = x.shape
+    if out is None:
+        out = torch.empty(t, h, dtype=_BF16, device=x.device)
+    if residual is not None:
+        assert residual.is_contiguous()
+        if residual_out is None:
+            residual_out = residual  # in place, like the reference's fused_add_rms_norm
+    L = _lib.load()
+    rc = L.gllm_rmsnorm(_p(x), _p(residual), _p(w), _p(out), _p(residual_out), t, h, x.stride(0), float(eps),
+                        stream_ptr())
+    check(rc, "rmsnorm")
+    _count()
+    return out, residual_out
+
+
+def silu_and_mul(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    assert x.dtype == _BF16 and x.dim() == 2 and x.stride(1) == 1
+    t, two_i = x.shape
+    i = two_i // 2
+    if out is None:
+        out = torch.empty(t, i, dtype=_BF16, device=x.device)
+    L = _lib.load()
+    check(L.gllm_silu_and_mul(_p(x), _p(out), t, i, x.stride(0), stream_ptr()), "silu_and_mul")
+    _count()
+    return out
+
+
+def embedding(ids: torch.Tensor, table: torch.Tensor, vocab_start: int = 0, vocab_end: Optional[int] = None,
+              out: Optional[torch.Tensor] = None):
+    assert ids.dtype == torch.int32 and table.dtype == _BF16 and table.is_contiguous()
+    t = ids.shape[0]
+    h = table.shape[1]
+    vocab_end = vocab_start + table.shape[0] if vocab_end is None else vocab_end
+    if out is None:
+        out = torch.empty(t, h, dtype=_BF16, device=table.device)
+    L = _lib.load()
+    check(L.gllm_embedding(_p(ids), _p(table), _p(out), t, h, vocab_start, vocab_end, stream_ptr()), "embedding")
+    _count()
+    return out
+
+
+def gather_rows(src: torch.Tensor, idx: torch.Tensor, out: Optional[torch.Tensor] = None):
+    assert src.dtype == _BF16 and src.is_contiguous() and idx.dtype == torch.int32
+    n, h = idx.shape[0], src.shape[1]
+    if out is None:
+        out = torch.empty(n, h, dtype=_BF16, device=src.device)
+    L = _lib.load()
+    check(L.gllm_gather_rows(_p(src), _p(idx), _p(out), n, h, stream_ptr()), "gather_rows")
+    _count()
+    return out
+
+
+# ----------------------------------------------------------------------------------------------
+# rope + kv write
+# ----------------------------------------------------------------------------------------------
+def rope_kv_write(q: torch.Tensor, k: torch.Tensor, v: Optional[torch.Tensor], positions: torch.Tensor,
+                  cos_sin: Optional[torch.Tensor], rot_dim: int, neox: bool,
+                  q_norm_w: Optional[torch.Tensor], k_norm_w: Optional[torch.Tensor], eps: float,
+                  k_cache: Optional[torch.Tensor], v_cache: Optional[torch.Tensor],
+                  slots: Optional[torch.Tensor], mrope_section=None):
+    """q [T,Hq,D], k [T,Hkv,D], v [T,Hkv,D] strided views (unit inner stride); in place."""
+    assert q.dtype == _BF16 and q.stride(2) == 1 and k.stride(2) == 1
+    t, hq, d = q.shape
+    hkv = k.shape[1]
+    if t == 0:
+        return
+    page_size = k_cache.shape[3] if k_cache is not None else 16
+    if cos_sin is not None:
+        assert cos_sin.dtype == torch.float32 and cos_sin.is_contiguous()
+    assert positions.dtype == torch.int32
+    sec0 = sec1 = 0
+    if mrope_section is not None and positions.dim() == 2:
+        sec0, sec1 = int(mrope_section[0]), int(mrope_section[1])
+        assert positions.is_contiguous()
+    L = _lib.load()
+    rc = L.gllm_rope_kv_write(
+        _p(q), q.stride(0), q.stride(1), hq, _p(k), k.stride(0), k.stride(1), hkv,
+        _p(v), v.stride(0) if v is not None else 0, v.stride(1) if v is not None else 0,
+        _p(q_norm_w), _p(k_norm_w), _p(cos_sin), d, rot_dim if cos_sin is not None else 0, 1 if neox else 0, t,
+        _p(positions), _p(slots), float(eps), _p(k_cache), _p(v_cache), sec0, sec1, page_size, stream_ptr())
+    check(rc, "rope_kv_write")
+    _count()
+
+
+# ----------------------------------------------------------------------------------------------
+# paged attention
+# ----------------------------------------------------------------------------------------------
+_attn_ws = {}
+
+
+def decode_splits(num_seqs: int, num_kv_heads: int, num_q_heads: int, max_seq_len: int) -> int:
+    g = num_q_heads // num_kv_heads
+    gp = max(d for d in range(1, min(g, 16) + 1) if g % d == 0)
+    ctas = num_seqs * num_kv_heads * (g // gp)
+    target = 4 * NUM_SMS
+    s = max(1, min(16, -(-target // max(ctas, 1))))
+    max_tiles = max(1, -(-max_seq_len // 64))
+    return max(1, min(s, max_tiles))
+
+
+def _workspace(device, n_floats: int, tag: str) -> torch.Tensor:
+    key = (device, tag)
+    ws = _attn_ws.get(key)
+    if ws is None or ws.numel() < n_floats:
+        ws = torch.empty(max(n_floats, 1 << 20), dtype=torch.float32, device=device)
+        _attn_ws[key] = ws
+    return ws
+
+
+def reserve_attn_workspace(device, max_seqs: int, num_q_heads: int, head_dim: int, max_splits: int = 16):
+    """Pre-size the split-KV workspace (call before CUDA-graph capture so pointers stay fixed)."""
+    _workspace(device, max_seqs * num_q_heads * max_splits * head_dim, "part_o")
+    _workspace(device, max_seqs * num_q_heads * max_splits, "part_lse")
+
+
+def paged_attention(q: torch.Tensor, k_cache: torch.Tensor, v_cache: torch.Tensor, block_table: torch.Tensor,
+                    seq_lens: torch.Tensor, query_start_loc: torch.Tensor, scale: float, num_q_heads: int,
+                    head_dim: int, num_decode_seqs: int, num_seqs: int, max_q_len: int, max_seq_len: int,
+                    out: Optional[torch.Tensor] = None, splits: Optional[int] = None) -> torch.Tensor:
+    """Mixed batch, decode sequences first (one token each), then prefill chunks.
+    q [T, Hq*D] (row stride arbitrary); caches [pages, Hkv, D/64, page, 64]."""
+    assert q.dtype == _BF16 and q.stride(1) == 1
+    t = q.shape[0]
+    hq, d = num_q_heads, head_dim
+    pages, hkv, nslab, page_size, w = k_cache.shape
+    assert w == 64 and nslab * 64 == d, "sm100 attention needs head_dim % 64 == 0"
+    assert block_table.dtype == torch.int32 and seq_lens.dtype == torch.int32
+    if out is None:
+        out = torch.empty(t, hq * d, dtype=_BF16, device=q.device)
+    L = _lib.load()
+    st = stream_ptr()
+    max_blocks = block_table.shape[1]
+    if num_decode_seqs > 0:
+        if splits is None:
+            splits = decode_splits(num_decode_seqs, hkv, hq, max_seq_len)
+        part_o = part_lse = None
+        if splits > 1:
+            part_o = _workspace(q.device, num_decode_seqs * hq * splits * d, "part_o")
+            part_lse = _workspace(q.device, num_decode_seqs * hq * splits, "part_lse")
+        rc = L.gllm_attn_decode(_p(q), q.stride(0), _p(out), _p(k_cache), _p(v_cache), pages, _p(block_table),
+                                _p(seq_lens), _p(part_o), _p(part_lse), num_decode_seqs, 0, max_blocks, hq, hkv, d,
+                                page_size, splits, float(scale), st)
+        check(rc, "attn_decode")
+        _count(2 if splits > 1 else 1)
+    n_prefill = num_seqs - num_decode_seqs
+    if n_prefill > 0:
+        assert query_start_loc.dtype == torch.int32
+        rc = L.gllm_attn_prefill(_p(q), q.stride(0), _p(out), _p(k_cache), _p(v_cache), pages, _p(block_table),
+                                 _p(seq_lens), _p(query_start_loc), n_prefill, num_decode_seqs, max_q_len,
+                                 max_blocks, hq, hkv, d, page_size, float(scale), st)
+        check(rc, "attn_prefill")
+        _count()
+    return out
+
+
+# ----------------------------------------------------------------------------------------------
+# sampling
+# ----------------------------------------------------------------------------------------------
+def sample(logits: torch.Tensor, temperature=None, top_k=None, top_p=None, rep_penalty=None,
+           seen_bits: Optional[torch.Tensor] = None, seed: int = 0, step: Optional[torch.Tensor] = None,
+           out: Optional[torch.Tensor] = None, out_max: Optional[torch.Tensor] = None,
+           vocab_offset: int = 0) -> torch.Tensor:
+    """logits [B, V] bf16/fp32; per-row params fp32/int32 tensors or None. seen_bits: uint32/int32
+    bitmask [B, ceil(V/32)] of tokens subject to the repetition penalty."""
+    assert logits.dim() == 2 and logits.stride(1) == 1
+    b, v = logits.shape
+    dtype = 0 if logits.dtype == _BF16 else 1
+    assert logits.dtype in (_BF16, torch.float32)
+    if out is None:
+        out = torch.empty(b, dtype=torch.int32, device=logits.device)
+    seen_words = seen_bits.shape[1] if seen_bits is not None else 0
+    L = _lib.load()
+    rc = L.gllm_sample(_p(logits), dtype, logits.stride(0), _p(out), b, v, _p(temperature), _p(top_k), _p(top_p),
+                       _p(rep_penalty), _p(seen_bits), seen_words, ctypes.c_uint64(seed & ((1 << 64) - 1)),
+                       _p(step), _p(out_max), vocab_offset, stream_ptr())
+    check(rc, "sample")
+    _count()
+    return out
+
+
+def mark_seen(seen_bits: torch.Tensor, rows: torch.Tensor, tokens: torch.Tensor):
+    assert rows.dtype == torch.int32 and tokens.dtype == torch.int32
+    L = _lib.load()
+    check(L.gllm_mark_seen(_p(seen_bits), seen_bits.shape[1], _p(rows), _p(tokens), rows.numel(), stream_ptr()),
+          "mark_seen")
+    _count()

@@ -1,0 +1,253 @@
+"""sm_100a kernels vs the PyTorch fp32 oracle (runs on the B200 box: `pytest -m gpu`)."""
+import math
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from gllm_b200.ops import ref
+
+
+def _dev():
+    return torch.device("cuda:0")
+
+
+def _rel_err(a, b):
+    a, b = a.float(), b.float()
+    return ((a - b).norm() / (b.norm() + 1e-12)).item()
+
+
+@pytest.mark.parametrize("m,n,k", [(128, 256, 64), (1, 512, 128), (37, 384, 192), (256, 6144, 4096),
+                                   (1000, 4096, 4096), (2048, 24576, 4096), (5, 151936, 1024),
+                                   (130, 72, 320)])
+@pytest.mark.parametrize("bn", [0, 32, 64, 128, 256])
+def test_gemm_bf16(m, n, k, bn, monkeypatch):
+    from gllm_b200.ops import sm100
+    if bn and m * n * k > 2e10:
+        pytest.skip("big shape only with auto tile")
+    monkeypatch.setattr(sm100, "_FORCE_BN", bn)
+    torch.manual_seed(0)
+    x = (torch.randn(m, k, device=_dev()) * 0.5).bfloat16()
+    w = (torch.randn(n, k, device=_dev()) * 0.05).bfloat16()
+    y = sm100.linear(x, w)
+    torch.cuda.synchronize()
+    yr = x.float() @ w.float().t()
+    assert _rel_err(y, yr) < 6e-3, _rel_err(y, yr)
+    assert torch.isfinite(y.float()).all()
+
+
+def test_gemm_bias_and_strided():
+    from gllm_b200.ops import sm100
+    torch.manual_seed(1)
+    m, n, k = 300, 1024, 512
+    big = (torch.randn(m, k * 2, device=_dev()) * 0.5).bfloat16()
+    x = big[:, :k]  # row stride 2k
+    w = (torch.randn(n, k, device=_dev()) * 0.05).bfloat16()
+    b = torch.randn(n, device=_dev()).bfloat16()
+    y = sm100.linear(x, w, b)
+    yr = x.float() @ w.float().t() + b.float()
+    assert _rel_err(y, yr) < 6e-3
+
+
+def test_gemm_silu_mul():
+    from gllm_b200.ops import sm100
+    torch.manual_seed(2)
+    m, i, k = 200, 1024, 512
+    x = (torch.randn(m, k, device=_dev()) * 0.5).bfloat16()
+    w = (torch.randn(2 * i, k, device=_dev()) * 0.05).bfloat16()
+    wi = ref.interleave_gate_up(w, 64)
+    y = sm100.linear_silu_mul(x, wi)
+    h = x.float() @ w.float().t()
+    yr = torch.nn.functional.silu(h[:, :i]) * h[:, i:]
+    assert _rel_err(y, yr) < 1e-2
+    # and the oracle's own interleaved path agrees
+    assert _rel_err(ref.linear_silu_mul(x, wi, 64), yr) < 1e-2
+
+
+@pytest.mark.parametrize("t,h", [(1, 4096), (7, 1024), (300, 4096), (64, 8192), (3, 7168), (2, 16384)])
+@pytest.mark.parametrize("add", [False, True])
+def test_rmsnorm(t, h, add):
+    from gllm_b200.ops import sm100
+    torch.manual_seed(3)
+    x = torch.randn(t, h, device=_dev()).bfloat16()
+    w = (1 + 0.1 * torch.randn(h, device=_dev())).bfloat16()
+    r = torch.randn(t, h, device=_dev()).bfloat16() if add else None
+    o_ref, r_ref = ref.rmsnorm(x, w, 1e-6, r.clone() if add else None)
+    o, r_out = sm100.rmsnorm(x, w, 1e-6, r.clone() if add else None)
+    assert _rel_err(o, o_ref) < 5e-3
+    if add:
+        assert _rel_err(r_out, r_ref) < 1e-3
+
+
+def test_silu_and_mul():
+    from gllm_b200.ops import sm100
+    x = torch.randn(77, 2 * 1536, device=_dev()).bfloat16()
+    assert _rel_err(sm100.silu_and_mul(x), ref.silu_and_mul(x)) < 5e-3
+
+
+def test_embedding_and_gather():
+    from gllm_b200.ops import sm100
+    table = torch.randn(1000, 512, device=_dev()).bfloat16()
+    ids = torch.randint(0, 2000, (333,), device=_dev(), dtype=torch.int32)
+    o = sm100.embedding(ids, table, 500, 1500)
+    o_ref = ref.embedding(ids, table, 500, 1500)
+    assert torch.equal(o, o_ref)
+    idx = torch.randint(0, 1000, (50,), device=_dev(), dtype=torch.int32)
+    assert torch.equal(sm100.gather_rows(table, idx), table[idx.long()])
+
+
+@pytest.mark.parametrize("d,rot,neox,qk_norm", [(128, 128, True, True), (128, 128, True, False),
+                                                (64, 64, True, False), (128, 64, False, False),
+                                                (256, 256, True, True)])
+def test_rope_kv_write(d, rot, neox, qk_norm):
+    from gllm_b200.ops import sm100
+    torch.manual_seed(4)
+    t, hq, hkv, page, pages = 83, 8, 2, 16, 32
+    qkv = torch.randn(t, (hq + 2 * hkv) * d, device=_dev()).bfloat16()
+    qkv_ref = qkv.clone()
+    pos = torch.randint(0, 500, (t,), device=_dev(), dtype=torch.int32)
+    slots = torch.randperm(pages * page, device=_dev())[:t].to(torch.int32)
+    slots[5] = -1
+    cs = ref.build_cos_sin_cache(rot, 512, 10000.0).to(_dev())
+    qn = (1 + 0.1 * torch.randn(d, device=_dev())).bfloat16() if qk_norm else None
+    kn = (1 + 0.1 * torch.randn(d, device=_dev())).bfloat16() if qk_norm else None
+    shape = ref.kv_cache_shape(pages, hkv, d, page)
+    kc, vc = torch.zeros(shape, device=_dev(), dtype=torch.bfloat16), torch.zeros(shape, device=_dev(), dtype=torch.bfloat16)
+    kc_r, vc_r = kc.clone(), vc.clone()
+
+    def views(buf):
+        q = buf[:, : hq * d].view(t, hq, d)
+        k = buf[:, hq * d: (hq + hkv) * d].view(t, hkv, d)
+        v = buf[:, (hq + hkv) * d:].view(t, hkv, d)
+        return q, k, v
+
+    q, k, v = views(qkv)
+    sm100.rope_kv_write(q, k, v, pos, cs, rot, neox, qn, kn, 1e-6, kc, vc, slots)
+    qr, kr, vr = views(qkv_ref)
+    ref.rope_kv_write(qr, kr, vr, pos, cs, rot, neox, qn, kn, 1e-6, kc_r, vc_r, slots)
+    assert _rel_err(qkv, qkv_ref) < 8e-3
+    assert _rel_err(kc, kc_r) < 8e-3
+    assert torch.equal(vc, vc_r)
+
+
+def test_rope_mrope():
+    from gllm_b200.ops import sm100
+    torch.manual_seed(5)
+    t, hq, hkv, d = 40, 4, 2, 128
+    q = torch.randn(t, hq, d, device=_dev()).bfloat16()
+    k = torch.randn(t, hkv, d, device=_dev()).bfloat16()
+    q_r, k_r = q.clone(), k.clone()
+    pos = torch.randint(0, 300, (3, t), device=_dev(), dtype=torch.int32)
+    cs = ref.build_cos_sin_cache(d, 512, 1e6).to(_dev())
+    sec = [16, 24, 24]
+    sm100.rope_kv_write(q, k, None, pos, cs, d, True, None, None, 1e-6, None, None, None, mrope_section=sec)
+    ref.rope_kv_write(q_r, k_r, None, pos, cs, d, True, None, None, 1e-6, None, None, None, mrope_section=sec)
+    assert _rel_err(q, q_r) < 8e-3 and _rel_err(k, k_r) < 8e-3
+
+
+def _make_paged(seq_lens, q_lens, hq, hkv, d, page, device, seed=0):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    b = len(seq_lens)
+    max_blocks = max((s + page - 1) // page for s in seq_lens) + 1
+    n_pages = sum((s + page - 1) // page for s in seq_lens) + 3
+    perm = torch.randperm(n_pages, generator=g).tolist()
+    bt = torch.zeros(b, max_blocks, dtype=torch.int32)
+    c = 0
+    for i, s in enumerate(seq_lens):
+        n = (s + page - 1) // page
+        bt[i, :n] = torch.tensor(perm[c:c + n], dtype=torch.int32)
+        c += n
+    shape = ref.kv_cache_shape(n_pages, hkv, d, page)
+    kc = (torch.randn(shape, generator=g) * 0.5).bfloat16().to(device)
+    vc = (torch.randn(shape, generator=g) * 0.5).bfloat16().to(device)
+    t = sum(q_lens)
+    q = (torch.randn(t, hq * d, generator=g) * 0.5).bfloat16().to(device)
+    qsl = torch.tensor([0] + list(torch.tensor(q_lens).cumsum(0)), dtype=torch.int32, device=device)
+    sl = torch.tensor(seq_lens, dtype=torch.int32, device=device)
+    return q, kc, vc, bt.to(device), sl, qsl
+
+
+@pytest.mark.parametrize("hq,hkv,d", [(32, 8, 128), (8, 8, 128), (28, 4, 128), (16, 2, 64), (8, 1, 128)])
+@pytest.mark.parametrize("splits", [None, 1, 4])
+def test_attn_decode(hq, hkv, d, splits):
+    from gllm_b200.ops import sm100
+    seq_lens = [1, 5, 16, 17, 63, 64, 65, 200, 1000, 333]
+    q_lens = [1] * len(seq_lens)
+    q, kc, vc, bt, sl, qsl = _make_paged(seq_lens, q_lens, hq, hkv, d, 16, _dev())
+    scale = 1.0 / math.sqrt(d)
+    o = sm100.paged_attention(q, kc, vc, bt, sl, qsl, scale, hq, d, len(seq_lens), len(seq_lens), 1,
+                              max(seq_lens), splits=splits)
+    torch.cuda.synchronize()
+    o_ref = ref.paged_attention(q, kc, vc, bt, sl, qsl, scale, hq, d)
+    assert torch.isfinite(o.float()).all()
+    assert _rel_err(o, o_ref) < 1e-2, _rel_err(o, o_ref)
+
+
+@pytest.mark.parametrize("hq,hkv,d", [(32, 8, 128), (8, 8, 128), (28, 4, 128), (16, 2, 64)])
+def test_attn_prefill_and_mixed(hq, hkv, d):
+    from gllm_b200.ops import sm100
+    # decode seqs first, then prefill chunks (some with prefix/chunk context)
+    seq_lens = [7, 130, 40, 300, 129, 64, 1024]
+    q_lens = [1, 1, 40, 100, 129, 3, 513]
+    nd = 2
+    q, kc, vc, bt, sl, qsl = _make_paged(seq_lens, q_lens, hq, hkv, d, 16, _dev(), seed=1)
+    scale = 1.0 / math.sqrt(d)
+    o = sm100.paged_attention(q, kc, vc, bt, sl, qsl, scale, hq, d, nd, len(seq_lens), max(q_lens), max(seq_lens))
+    torch.cuda.synchronize()
+    o_ref = ref.paged_attention(q, kc, vc, bt, sl, qsl, scale, hq, d)
+    assert torch.isfinite(o.float()).all()
+    assert _rel_err(o, o_ref) < 1e-2, _rel_err(o, o_ref)
+
+
+def test_sampler_greedy_and_filter():
+    from gllm_b200.ops import sm100
+    torch.manual_seed(6)
+    b, v = 33, 151936
+    logits = (torch.randn(b, v, device=_dev()) * 3).bfloat16()
+    tok = sm100.sample(logits)
+    assert torch.equal(tok.long(), logits.float().argmax(-1))
+    # temperature/top-k/top-p: every drawn token must lie in the oracle's support, and the
+    # empirical distribution over many draws must match on a small vocab
+    temp = torch.full((b,), 0.8, device=_dev())
+    tk = torch.full((b,), 50, device=_dev(), dtype=torch.int32)
+    tp = torch.full((b,), 0.9, device=_dev())
+    probs = ref.sample_filter(logits, temp, tk, tp)
+    for s in range(3):
+        tok = sm100.sample(logits, temp, tk, tp, seed=123 + s)
+        p_tok = probs.gather(1, tok.long().view(-1, 1))
+        assert (p_tok > 0).all()
+
+
+def test_sampler_distribution():
+    from gllm_b200.ops import sm100
+    torch.manual_seed(7)
+    v = 64
+    row = torch.randn(v, device=_dev()) * 2
+    n = 20000
+    logits = row.unsqueeze(0).repeat(n, 1).contiguous()
+    temp = torch.full((n,), 1.3, device=_dev())
+    tk = torch.full((n,), 20, device=_dev(), dtype=torch.int32)
+    tp = torch.full((n,), 0.85, device=_dev())
+    probs = ref.sample_filter(logits[:1], temp[:1], tk[:1], tp[:1])[0]
+    tok = sm100.sample(logits, temp, tk, tp, seed=99)
+    emp = torch.bincount(tok.long(), minlength=v).float() / n
+    assert (emp[probs == 0] == 0).all()
+    assert (emp - probs).abs().max().item() < 0.02
+
+
+def test_sampler_rep_penalty():
+    from gllm_b200.ops import sm100
+    torch.manual_seed(8)
+    b, v = 4, 1000
+    logits = torch.randn(b, v, device=_dev())
+    seen = torch.zeros(b, (v + 31) // 32, dtype=torch.int32, device=_dev())
+    top = logits.argmax(-1).to(torch.int32)
+    rows = torch.arange(b, device=_dev(), dtype=torch.int32)
+    sm100.mark_seen(seen, rows, top)
+    pen = torch.full((b,), 50.0, device=_dev())
+    tok = sm100.sample(logits, rep_penalty=pen, seen_bits=seen)
+    mask = torch.zeros(b, v, dtype=torch.bool, device=_dev())
+    mask[rows.long(), top.long()] = True
+    exp = ref.sample(logits, rep_penalty=pen, seen_mask=mask)
+    assert torch.equal(tok, exp)

@@ -1,0 +1,294 @@
+"""Continuous-batching scheduler with three policies (reference: gllm/scheduler.py:16-355):
+
+  * ``chunked_prefill``  — Sarathi-style: one token budget `maxp`; decode first, rest to prefill.
+  * ``split_pd``         — prefill-priority: decode budget is zeroed while prefills wait and KV
+                           headroom exists.
+  * ``token_throttling`` — gLLM (SC'25): prefill budget throttled by KV utilisation (UT) and by
+                           the amount of waiting work spread over `iterp` iterations (WT); decode
+                           budget = all running decode seqs balanced over the `pp_size`
+                           micro-batches in flight.
+
+Invariants kept from the reference: at most `pp_size` micro-batches in flight; each batch is
+**decode sequences first, then prefill chunks**; preemption = free KV + recompute; a sequence
+emits a token only once its whole prompt is computed.
+
+The budget computations are exposed as pure functions so they can be unit-tested against the
+formulas without an engine.
+"""
+from __future__ import annotations
+
+import random
+import time
+from collections import deque
+from dataclasses import dataclass, field
+from typing import Deque, List, Optional
+
+from gllm_b200.memory_manager import MemoryManager, PrefixMemoryManager
+from gllm_b200.sequence import Sequence
+from gllm_b200.utils.logging import logger
+
+
+# ------------------------------------------------------------------------------------------------
+# pure budget functions
+# ------------------------------------------------------------------------------------------------
+def balanced_decode_budget(num_total_decode_seqs: int, pp_size: int, maxd: int, rnd: Optional[int] = None) -> int:
+    """⌊(#running decode seqs + U[0,pp)) / pp⌋ capped by maxd (gllm/scheduler.py:192-203)."""
+    if num_total_decode_seqs < pp_size:
+        budget = 1
+    else:
+        r = random.randint(0, pp_size - 1) if rnd is None else rnd
+        budget = (num_total_decode_seqs + r) // pp_size
+    return min(maxd, budget)
+
+
+def kv_headroom_tokens(num_free_pages: int, num_kvthresh_pages: int, page_size: int) -> int:
+    return page_size * max(num_free_pages - num_kvthresh_pages, 0)
+
+
+def throttled_prefill_budget(headroom_tokens: int, world_size: int, free_ratio: float, kvthresh: float,
+                             maxp: int, minp: int, iterp: int, num_wait_seqs: int, num_wait_tokens: int) -> int:
+    """Token-throttling prefill budget #P (gllm/scheduler.py:299-320)."""
+    budget = headroom_tokens
+    if world_size > 1 and budget != 0:
+        ratio = max((free_ratio - kvthresh) / (1 - kvthresh), 0.0)
+        budget = min(round(ratio * maxp), budget)  # UT
+        if num_wait_seqs > 1:  # WT
+            budget = min(max(num_wait_tokens // iterp, minp), budget)
+    else:
+        budget = min(maxp, budget)
+    return budget
+
+
+class ScheduledSeq:
+    """One entry of a micro-batch: compute tokens [start, start + n) of `seq`."""
+    __slots__ = ("seq", "start", "n")
+
+    def __init__(self, seq: Sequence, start: int, n: int):
+        self.seq, self.start, self.n = seq, start, n
+
+    @property
+    def is_decode(self) -> bool:
+        return self.start >= self.seq.prompt_len
+
+    @property
+    def emits_token(self) -> bool:
+        return self.start + self.n >= self.seq.prompt_len
+
+    def __repr__(self):
+        return f"ScheduledSeq(id={self.seq.seq_id}, start={self.start}, n={self.n})"
+
+
+@dataclass
+class SchedulerOutput:
+    """What rank 0 tells the front-end after a batch finished (mirrors IPCPackage fields)."""
+    act_schedule_ids: List[int] = field(default_factory=list)
+    next_tokens: List[int] = field(default_factory=list)
+    free_ids: List[int] = field(default_factory=list)
+
+
+class Scheduler:
+    def __init__(self, memory_manager: MemoryManager, pp_size: int = 1, world_size: int = 1,
+                 schedule_method: str = "chunked_prefill", maxd: int = 2048, maxp: int = 2048, minp: int = 32,
+                 iterp: int = 8, kvthresh: float = 0.05, page_size: int = 16, log: bool = True):
+        assert schedule_method in ("chunked_prefill", "split_pd", "token_throttling"), schedule_method
+        self.mm = memory_manager
+        self.pp_size = pp_size
+        self.world_size = world_size
+        self.schedule_method = schedule_method
+        self.maxd, self.maxp, self.minp, self.iterp = maxd, maxp, minp, iterp
+        self.kvthresh = kvthresh
+        self.page_size = page_size
+        self.num_kvthresh_pages = int(kvthresh * self.mm.get_num_free_pages())
+        self.seqs_to_prefill: Deque[Sequence] = deque()
+        self.seqs_to_decode: Deque[Sequence] = deque()
+        self.batch_running: Deque[List[ScheduledSeq]] = deque()
+        self.next_tokens_queue: Deque[List[int]] = deque()
+        self.abort_ids = set()
+        self.num_preempt_seqs = 0
+        self._log_preempt_at = 10
+        self.num_wait_tokens = 0
+        self.log = log
+        self.log_time = 0.0
+        self.last_stats = {}
+
+    # -- inputs -----------------------------------------------------------------------------------
+    def add_new_requests(self, seqs: List[Sequence]):
+        self.seqs_to_prefill.extend(seqs)
+
+    def add_abort_ids(self, ids):
+        self.abort_ids.update(ids)
+
+    def add_next_tokens(self, next_tokens: List[int]):
+        self.next_tokens_queue.append(next_tokens)
+
+    def set_log(self, log: bool):
+        self.log = log
+
+    # -- state ------------------------------------------------------------------------------------
+    def has_work(self) -> bool:
+        return bool(self.seqs_to_decode or self.seqs_to_prefill or self.batch_running)
+
+    def get_num_decode_seqs(self) -> int:
+        # reference counts every seq of every in-flight batch (gllm/scheduler.py:64-68)
+        return len(self.seqs_to_decode) + sum(len(b) for b in self.batch_running)
+
+    def update_num_wait_tokens(self):
+        self.num_wait_tokens = sum(len(s) - s.scheduled_token_num for s in self.seqs_to_prefill)
+
+    # -- outputs ----------------------------------------------------------------------------------
+    def process_output(self) -> Optional[SchedulerOutput]:
+        if not self.next_tokens_queue:
+            return None
+        batch = self.batch_running.popleft()
+        next_tokens = self.next_tokens_queue.popleft()
+        out = SchedulerOutput()
+        for idx, ent in enumerate(batch):
+            seq = ent.seq
+            if seq.is_abort:
+                if seq.page_table:
+                    self.mm.free(seq)
+                    out.free_ids.append(seq.seq_id)
+                self.abort_ids.discard(seq.seq_id)
+                continue
+            seq.computed_token_num = max(seq.computed_token_num, ent.start + ent.n)
+            if seq.computed_prompt:
+                tok = int(next_tokens[idx])
+                out.act_schedule_ids.append(seq.seq_id)
+                out.next_tokens.append(tok)
+                seq.append(tok)
+                if seq.is_finish:
+                    out.free_ids.append(seq.seq_id)
+                    self.mm.free(seq)
+                else:
+                    self.seqs_to_decode.appendleft(seq)
+            # else: unfinished prefill — its continuation is already at the head of seqs_to_prefill
+        return out
+
+    def check_abort_seqs(self) -> Optional[SchedulerOutput]:
+        if not self.abort_ids:
+            return None
+        out = SchedulerOutput()
+        inflight = {id(e.seq) for b in self.batch_running for e in b}
+        for q in (self.seqs_to_prefill, self.seqs_to_decode):
+            for seq in list(q):
+                if seq.seq_id in self.abort_ids:
+                    q.remove(seq)
+                    seq.is_abort = True
+                    if id(seq) in inflight:
+                        continue  # a chunk is still in flight: freed when that batch returns
+                    out.free_ids.append(seq.seq_id)
+                    self.mm.free(seq)
+                    self.abort_ids.discard(seq.seq_id)
+        for batch in self.batch_running:
+            for ent in batch:
+                if ent.seq.seq_id in self.abort_ids:
+                    ent.seq.is_abort = True
+        return out if out.free_ids else None
+
+    # -- scheduling -------------------------------------------------------------------------------
+    def can_schedule(self) -> bool:
+        return bool(self.seqs_to_decode or self.seqs_to_prefill) and len(self.batch_running) < self.pp_size
+
+    def schedule_once(self) -> List["ScheduledSeq"]:
+        if not self.can_schedule():
+            return []
+        seqs = self.token_throttling() if self.schedule_method == "token_throttling" else self.chunked_prefill()
+        if seqs:
+            self.batch_running.append(seqs)
+        return seqs
+
+    def check_preempt(self, num_pages_to_allocate: int):
+        preempted = []
+        while self.mm.get_num_free_pages() < num_pages_to_allocate and self.seqs_to_decode:
+            seq = self.seqs_to_decode.popleft()
+            self.mm.free(seq)
+            seq.preempt()
+            preempted.append(seq)
+        if preempted:
+            self.seqs_to_prefill.extendleft(preempted)
+            self.num_preempt_seqs += len(preempted)
+            if self.num_preempt_seqs >= self._log_preempt_at:
+                self._log_preempt_at *= 2
+                logger.warning("#Preempted seqs: %d, try increasing --kvthresh or performance will be poor!",
+                               self.num_preempt_seqs)
+
+    def schedule_decode_batch(self, budget: int) -> List["ScheduledSeq"]:
+        self.check_preempt(min(budget, len(self.seqs_to_decode)))
+        batch = []
+        seqs = []
+        for _ in range(budget):
+            if not self.seqs_to_decode:
+                break
+            seq = self.seqs_to_decode.popleft()
+            start = seq.computed_token_num
+            seq.scheduled_token_num = start + 1
+            batch.append(ScheduledSeq(seq, start, 1))
+            seqs.append(seq)
+        self.mm.pre_allocate_page(seqs)
+        return batch
+
+    def schedule_prefill_batch(self, budget: int):
+        batch: List[ScheduledSeq] = []
+        n_tokens = 0
+        while self.seqs_to_prefill and budget > 0:
+            seq = self.seqs_to_prefill[0]
+            if isinstance(self.mm, PrefixMemoryManager) and seq.scheduled_token_num == 0 and not seq.page_table:
+                self.mm.pre_allocate_computed_page([seq])
+            start = seq.scheduled_token_num
+            remaining = len(seq) - start
+            take = min(remaining, budget)
+            seq.scheduled_token_num = start + take
+            if self.mm.pages_needed(seq) > self.mm.get_num_free_pages():
+                seq.scheduled_token_num = start
+                break  # no KV room right now
+            self.mm.pre_allocate_page([seq])
+            n_tokens += take
+            budget -= take
+            batch.append(ScheduledSeq(seq, start, take))
+            if take == remaining:
+                self.seqs_to_prefill.popleft()
+            # else: unfinished prefill stays at the queue head and continues with its next chunk —
+            # possibly while this one is still in flight when pp_size > 1 (the reference deep-copies
+            # the sequence for that, gllm/scheduler.py:226-231)
+        return batch, n_tokens
+
+    def chunked_prefill(self) -> List["ScheduledSeq"]:
+        budget = self.maxp
+        num_total_decode = self.get_num_decode_seqs()
+        decode_budget = min(balanced_decode_budget(num_total_decode, self.pp_size, self.maxd), budget)
+        if self.schedule_method == "split_pd" and self.seqs_to_prefill and \
+                self.mm.get_num_free_pages() >= self.num_kvthresh_pages:
+            decode_budget = 0
+        decode_batch = self.schedule_decode_batch(decode_budget)
+        budget -= len(decode_batch)
+        budget = min(budget, kv_headroom_tokens(self.mm.get_num_free_pages(), self.num_kvthresh_pages,
+                                                 self.page_size))
+        prefill_batch, n_prefill = self.schedule_prefill_batch(budget)
+        self._log_status(num_total_decode, n_prefill, len(decode_batch))
+        return decode_batch + prefill_batch
+
+    def token_throttling(self) -> List["ScheduledSeq"]:
+        headroom = kv_headroom_tokens(self.mm.get_num_free_pages(), self.num_kvthresh_pages, self.page_size)
+        if self.world_size > 1 and headroom != 0:
+            self.update_num_wait_tokens()
+        budget = throttled_prefill_budget(headroom, self.world_size, self.mm.get_memory_free(), self.kvthresh,
+                                          self.maxp, self.minp, self.iterp, len(self.seqs_to_prefill),
+                                          self.num_wait_tokens)
+        prefill_batch, n_prefill = self.schedule_prefill_batch(budget)
+        num_total_decode = self.get_num_decode_seqs()
+        decode_budget = balanced_decode_budget(num_total_decode, self.pp_size, self.maxd)
+        decode_batch = self.schedule_decode_batch(decode_budget)
+        self._log_status(num_total_decode, n_prefill, len(decode_batch))
+        return decode_batch + prefill_batch
+
+    def _log_status(self, num_run: int, n_prefill: int, n_decode: int):
+        self.last_stats = {"wait": len(self.seqs_to_prefill), "run": num_run, "prefill_tokens": n_prefill,
+                           "decode_seqs": n_decode, "memory_util": self.mm.get_memory_util(),
+                           "cache_hit_rate": self.mm.get_cache_hit_rate(), "preempted": self.num_preempt_seqs}
+        if self.log and time.time() - self.log_time > 1:
+            self.log_time = time.time()
+            msg = "#wait: %4d #run: %4d #prefill: %4d #decode: %4d memory_util: %5.2f %%" % (
+                len(self.seqs_to_prefill), num_run, n_prefill, n_decode, self.mm.get_memory_util())
+            if isinstance(self.mm, PrefixMemoryManager):
+                msg += " cache_hit_rate: %5.2f %%" % self.mm.get_cache_hit_rate()
+            logger.info(msg)

@@ -207,16 +207,25 @@ def test_sampler_greedy_and_filter():
     logits = (torch.randn(b, v, device=_dev()) * 3).bfloat16()
     tok = sm100.sample(logits)
     assert torch.equal(tok.long(), logits.float().argmax(-1))
-    # temperature/top-k/top-p: every drawn token must lie in the oracle's support, and the
-    # empirical distribution over many draws must match on a small vocab
+    # temperature/top-k/top-p: every drawn token must lie in the oracle's support. fp32 logits so
+    # that ties (which the kernel keeps, the sort-based oracle breaks arbitrarily) are improbable;
+    # the oracle gets a hair more top-p mass to absorb x*(1/T) vs x/T rounding at the boundary.
+    logits = torch.randn(b, v, device=_dev()) * 3
     temp = torch.full((b,), 0.8, device=_dev())
     tk = torch.full((b,), 50, device=_dev(), dtype=torch.int32)
     tp = torch.full((b,), 0.9, device=_dev())
-    probs = ref.sample_filter(logits, temp, tk, tp)
+    probs = ref.sample_filter(logits, temp, tk + 1, tp + 1e-3)
     for s in range(3):
         tok = sm100.sample(logits, temp, tk, tp, seed=123 + s)
         p_tok = probs.gather(1, tok.long().view(-1, 1))
         assert (p_tok > 0).all()
+    # top-p only (no top-k) and top-k only
+    tok = sm100.sample(logits, temp, torch.full((b,), -1, device=_dev(), dtype=torch.int32), tp, seed=5)
+    probs = ref.sample_filter(logits, temp, None, tp + 1e-3)
+    assert (probs.gather(1, tok.long().view(-1, 1)) > 0).all()
+    tok = sm100.sample(logits, temp, tk, None, seed=6)
+    probs = ref.sample_filter(logits, temp, tk + 1, None)
+    assert (probs.gather(1, tok.long().view(-1, 1)) > 0).all()
 
 
 def test_sampler_distribution():

@@ -117,12 +117,13 @@ __global__ void __launch_bounds__(kSampleThreads)
 sample_kernel(const T* __restrict__ logits, int64_t ld, int V, const float* __restrict__ temperature,
               const int32_t* __restrict__ top_k, const float* __restrict__ top_p,
               const float* __restrict__ rep_penalty, const uint32_t* __restrict__ seen, int seen_words,
-              uint64_t seed, const int64_t* __restrict__ step_ptr, int32_t* __restrict__ out_tokens,
+              const int32_t* __restrict__ slot_idx, uint64_t seed, const int64_t* __restrict__ step_ptr, int32_t* __restrict__ out_tokens,
               float* __restrict__ out_max, int vocab_offset) {
   __shared__ BlockScratch S;
   const int row = blockIdx.x;
   const T* lr = logits + static_cast<size_t>(row) * ld;
-  const uint32_t* seen_row = seen != nullptr ? seen + static_cast<size_t>(row) * seen_words : nullptr;
+  const uint32_t* seen_row =
+      seen != nullptr ? seen + static_cast<size_t>(slot_idx != nullptr ? slot_idx[row] : row) * seen_words : nullptr;
   const float temp = temperature != nullptr ? temperature[row] : 1.0f;
   const float inv_temp = (temp <= 1e-5f) ? 1.0f : 1.0f / temp;
   const float pen = rep_penalty != nullptr ? rep_penalty[row] : 1.0f;
@@ -260,7 +261,8 @@ using namespace b200;
 // mixed into the RNG stream so CUDA-graph replays draw fresh numbers.
 GLLM_EXPORT int gllm_sample(const void* logits, int dtype, int64_t ld, void* out_tokens, int B, int V,
                             const void* temperature, const void* top_k, const void* top_p,
-                            const void* rep_penalty, const void* seen, int seen_words, uint64_t seed,
+                            const void* rep_penalty, const void* seen, int seen_words,
+                            const void* slot_idx, uint64_t seed,
                             const void* step_ptr, void* out_max, int vocab_offset, void* stream) {
   if (B <= 0) return 0;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
@@ -268,14 +270,16 @@ GLLM_EXPORT int gllm_sample(const void* logits, int dtype, int64_t ld, void* out
     sample_kernel<__nv_bfloat16><<<B, kSampleThreads, 0, st>>>(
         reinterpret_cast<const __nv_bfloat16*>(logits), ld, V, reinterpret_cast<const float*>(temperature),
         reinterpret_cast<const int32_t*>(top_k), reinterpret_cast<const float*>(top_p),
-        reinterpret_cast<const float*>(rep_penalty), reinterpret_cast<const uint32_t*>(seen), seen_words, seed,
+        reinterpret_cast<const float*>(rep_penalty), reinterpret_cast<const uint32_t*>(seen), seen_words,
+        reinterpret_cast<const int32_t*>(slot_idx), seed,
         reinterpret_cast<const int64_t*>(step_ptr), reinterpret_cast<int32_t*>(out_tokens),
         reinterpret_cast<float*>(out_max), vocab_offset);
   } else {
     sample_kernel<float><<<B, kSampleThreads, 0, st>>>(
         reinterpret_cast<const float*>(logits), ld, V, reinterpret_cast<const float*>(temperature),
         reinterpret_cast<const int32_t*>(top_k), reinterpret_cast<const float*>(top_p),
-        reinterpret_cast<const float*>(rep_penalty), reinterpret_cast<const uint32_t*>(seen), seen_words, seed,
+        reinterpret_cast<const float*>(rep_penalty), reinterpret_cast<const uint32_t*>(seen), seen_words,
+        reinterpret_cast<const int32_t*>(slot_idx), seed,
         reinterpret_cast<const int64_t*>(step_ptr), reinterpret_cast<int32_t*>(out_tokens),
         reinterpret_cast<float*>(out_max), vocab_offset);
   }

@@ -1,0 +1,160 @@
+"""Control-plane IPC over ZeroMQ (reference: gllm/comm.py:34-190).
+
+Channels (all PUSH/PULL, HWM 0):
+    front-end -> driver      requests / aborts / control commands          (pickled IPCPackage)
+    driver    -> front-end   sampled tokens / freed ids                    (pickled IPCPackage)
+    driver    -> every peer  one scheduled micro-batch per message         (header + raw arrays)
+    output rank -> driver    sampled tokens of a finished micro-batch
+
+Differences from the reference: a micro-batch travels as flat numpy buffers (`BatchArrays`),
+not as pickled `Sequence` objects that every rank re-expands in Python; sends are issued from the
+calling thread (zmq queues them on its IO thread) instead of a new Python thread per message
+(gllm/comm.py:166-167), which also keeps per-socket ordering.
+"""
+from __future__ import annotations
+
+import os
+import pickle
+import uuid
+from dataclasses import dataclass, field
+from typing import List, Optional
+
+import numpy as np
+import zmq
+
+from gllm_b200.input_data import BatchArrays
+
+
+@dataclass
+class IPCPackage:
+    """Front-end <-> driver message (reference: gllm/comm.py:21-31)."""
+    schedule_lists: list = field(default_factory=list)   # new Sequence objects (front-end -> driver)
+    abort_ids: list = field(default_factory=list)
+    act_schedule_ids: list = field(default_factory=list)  # driver -> front-end
+    next_tokens: list = field(default_factory=list)
+    free_ids: list = field(default_factory=list)
+    control_cmd: Optional[tuple] = None
+    stats: Optional[dict] = None
+
+
+def make_socket(ctx: zmq.Context, kind: int, addr: str, bind: bool) -> zmq.Socket:
+    s = ctx.socket(kind)
+    s.setsockopt(zmq.LINGER, 0)
+    if kind == zmq.PUSH:
+        s.setsockopt(zmq.SNDHWM, 0)
+        s.setsockopt(zmq.SNDBUF, 64 << 20)
+    else:
+        s.setsockopt(zmq.RCVHWM, 0)
+        s.setsockopt(zmq.RCVBUF, 64 << 20)
+    if bind:
+        s.bind(addr)
+    else:
+        s.connect(addr)
+    return s
+
+
+def ipc_base(tag: Optional[str] = None) -> str:
+    tag = tag or uuid.uuid4().hex[:12]
+    return f"ipc:///tmp/gllm_b200_{tag}"
+
+
+class Comm:
+    """One instance per process. `role` in {"frontend", "driver", "peer"} (a process can be both
+    front-end and driver when the engine runs in-process: then the front-end channel is bypassed)."""
+
+    def __init__(self, base: str, rank: int, world_size: int, output_rank: int, frontend: bool = False,
+                 tcp_host: Optional[str] = None, port_base: int = 8002, master_addr: str = "127.0.0.1"):
+        self.base, self.rank, self.world_size, self.output_rank = base, rank, world_size, output_rank
+        self.frontend = frontend
+        self.tcp_host, self.port_base, self.master_addr = tcp_host, port_base, master_addr
+        self.ctx = zmq.Context.instance()
+        self.sock_fe_in = self.sock_fe_out = None
+        self.batch_out: List[zmq.Socket] = []
+        self.batch_in = None
+        self.tok_in = self.tok_out = None
+
+    # addresses ---------------------------------------------------------------------------------
+    def _addr(self, name: str, idx: int = 0) -> str:
+        if self.tcp_host is not None:
+            # multi-node: deterministic port per channel (reference: zmq_port_base + rank)
+            table = {"fe_req": 0, "fe_out": 1, "tok": 2}
+            port = self.port_base + (table[name] if name in table else 3 + idx)
+            host = self.master_addr if name in table else "*"
+            return f"tcp://{host}:{port}"
+        return f"{self.base}_{name}_{idx}"
+
+    def init(self):
+        P, L = zmq.PUSH, zmq.PULL
+        if self.frontend:
+            self.sock_fe_out = make_socket(self.ctx, P, self._addr("fe_req"), bind=False)
+            self.sock_fe_in = make_socket(self.ctx, L, self._addr("fe_out"), bind=True)
+            return self
+        if self.rank == 0:
+            self.sock_fe_in = make_socket(self.ctx, L, self._addr("fe_req"), bind=True)
+            self.sock_fe_out = make_socket(self.ctx, P, self._addr("fe_out"), bind=False)
+            for r in range(1, self.world_size):
+                self.batch_out.append(make_socket(self.ctx, P, self._peer_addr(r, connect=True), bind=False))
+            if self.output_rank != 0:
+                self.tok_in = make_socket(self.ctx, L, self._addr("tok"), bind=True)
+        else:
+            self.batch_in = make_socket(self.ctx, L, self._peer_addr(self.rank, connect=False), bind=True)
+            if self.rank == self.output_rank:
+                addr = self._addr("tok")
+                self.tok_out = make_socket(self.ctx, P, addr.replace("*", self.master_addr), bind=False)
+        return self
+
+    def _peer_addr(self, r: int, connect: bool) -> str:
+        if self.tcp_host is not None:
+            host = self.peer_hosts[r] if connect and getattr(self, "peer_hosts", None) else "*"
+            return f"tcp://{host}:{self.port_base + 3 + r}"
+        return f"{self.base}_batch_{r}"
+
+    # front-end <-> driver ----------------------------------------------------------------------
+    def send_frontend(self, pkg: IPCPackage):
+        self.sock_fe_out.send(pickle.dumps(pkg, protocol=pickle.HIGHEST_PROTOCOL))
+
+    def recv_frontend(self) -> List[IPCPackage]:
+        out = []
+        while self.sock_fe_in is not None and self.sock_fe_in.poll(timeout=0):
+            out.append(pickle.loads(self.sock_fe_in.recv()))
+        return out
+
+    # driver -> peers -----------------------------------------------------------------------------
+    def send_batch(self, batch: BatchArrays, ranks: Optional[List[int]] = None):
+        if not self.batch_out:
+            return
+        hdr, bufs = batch.to_wire()
+        frames = [pickle.dumps(("batch", hdr), protocol=pickle.HIGHEST_PROTOCOL)] + bufs
+        for r, s in enumerate(self.batch_out, start=1):
+            if ranks is None or r in ranks:
+                s.send_multipart(frames, copy=False)
+
+    def broadcast_control(self, cmd: tuple):
+        frames = [pickle.dumps(("control", cmd), protocol=pickle.HIGHEST_PROTOCOL)]
+        for s in self.batch_out:
+            s.send_multipart(frames)
+
+    def recv_batch(self, timeout_ms: int = 0):
+        """-> ("batch", BatchArrays) | ("control", cmd) | None"""
+        if self.batch_in is None or not self.batch_in.poll(timeout=timeout_ms):
+            return None
+        frames = self.batch_in.recv_multipart(copy=False)
+        kind, payload = pickle.loads(frames[0].buffer)
+        if kind == "batch":
+            return "batch", BatchArrays.from_wire(payload, [f.buffer for f in frames[1:]])
+        return kind, payload
+
+    # output rank -> driver -----------------------------------------------------------------------
+    def send_tokens(self, batch_id: int, tokens: List[int]):
+        self.tok_out.send(pickle.dumps((batch_id, tokens), protocol=pickle.HIGHEST_PROTOCOL))
+
+    def recv_tokens(self):
+        out = []
+        while self.tok_in is not None and self.tok_in.poll(timeout=0):
+            out.append(pickle.loads(self.tok_in.recv()))
+        return out
+
+    def close(self):
+        for s in [self.sock_fe_in, self.sock_fe_out, self.batch_in, self.tok_in, self.tok_out, *self.batch_out]:
+            if s is not None:
+                s.close(0)

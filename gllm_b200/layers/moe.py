@@ -1,0 +1,157 @@
+"""Mixture-of-experts block: router -> top-k -> experts (EP or TP sharded) [+ shared expert].
+
+Reference: gllm/layers/moe/fused_moe_triton/layer.py:197-369 (FusedMoE), gllm/models/qwen2_moe.py:35-89,
+gllm/models/mixtral.py:28-54. Sharding follows the reference: with EP (default when tp > 1) every
+rank holds `E / ep` whole experts (contiguous block, remainder on the last rank); without EP every
+rank holds all experts with `intermediate / tp` columns. The block returns the *partial* sum over
+this rank's experts; the caller reduces it over the TP group together with the following
+residual-add + RMSNorm (`TPComm.reduce_add_norm`).
+
+On CUDA the experts run as one grouped tcgen05 GEMM pair over expert-sorted token slots
+(csrc/moe/); the all-to-all dispatch/combine variant lives in parallel/fused.py.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+from torch import nn
+
+from gllm_b200.layers import functional as Fn
+from gllm_b200.models import weight_utils as wu
+from gllm_b200.ops import ref
+from gllm_b200.parallel import state as ps
+
+
+def _param(*shape, dtype, device):
+    return nn.Parameter(torch.empty(shape, dtype=dtype, device=device), requires_grad=False)
+
+
+class FusedMoE(nn.Module):
+    def __init__(self, num_experts: int, top_k: int, hidden: int, intermediate: int, dtype, device,
+                 renormalize: bool = True, use_ep: Optional[bool] = None, scoring: str = "softmax",
+                 n_group: int = 0, topk_group: int = 0, routed_scaling: float = 1.0, bias_correction: bool = False):
+        super().__init__()
+        st = ps.get_state()
+        self.num_experts, self.top_k, self.hidden = num_experts, top_k, hidden
+        self.renormalize, self.scoring = renormalize, scoring
+        self.n_group, self.topk_group, self.routed_scaling = n_group, topk_group, routed_scaling
+        self.tp_size, self.tp_rank = st.tp_size, st.tp_rank
+        self.use_ep = (st.ep_size > 1) if use_ep is None else (use_ep and st.tp_size > 1)
+        if self.use_ep:
+            self.e_start, self.e_local = wu.expert_range(num_experts, st.ep_rank, st.ep_size)
+            self.inter = intermediate
+            emap = torch.full((num_experts,), -1, dtype=torch.int32)
+            emap[self.e_start:self.e_start + self.e_local] = torch.arange(self.e_local, dtype=torch.int32)
+            self.register_buffer("expert_map", emap.to(device), persistent=False)
+        else:
+            self.e_start, self.e_local = 0, num_experts
+            assert intermediate % st.tp_size == 0
+            self.inter = intermediate // st.tp_size
+            self.expert_map = None
+        self.router_w = _param(num_experts, hidden, dtype=dtype, device=device)
+        self.e_bias = _param(num_experts, dtype=torch.float32, device=device) if bias_correction else None
+        self.w13 = _param(self.e_local, 2 * self.inter, hidden, dtype=dtype, device=device)
+        self.w2 = _param(self.e_local, hidden, self.inter, dtype=dtype, device=device)
+
+    # -- routing ----------------------------------------------------------------------------------
+    def route(self, h: torch.Tensor):
+        logits = Fn.linear(h, self.router_w)
+        if self.n_group > 0:
+            return ref.grouped_topk(logits, self.top_k, self.renormalize, self.n_group, self.topk_group,
+                                    self.scoring, self.e_bias, self.routed_scaling) if not h.is_cuda else \
+                _sm_grouped_topk(self, logits)
+        if h.is_cuda:
+            from gllm_b200.ops import sm100_moe
+            return sm100_moe.topk_softmax(logits, self.top_k, self.renormalize)
+        return ref.topk_softmax(logits, self.top_k, self.renormalize)
+
+    def forward(self, h: torch.Tensor, tpc=None) -> torch.Tensor:
+        w, ids = self.route(h)
+        if h.is_cuda:
+            from gllm_b200.ops import sm100_moe
+            return sm100_moe.fused_experts(h, self.w13, self.w2, w, ids, self.expert_map)
+        return ref.fused_experts(h, self.w13, self.w2, w, ids, self.expert_map)
+
+    # -- weights ----------------------------------------------------------------------------------
+    def load_expert(self, global_e: int, gate: torch.Tensor, up: torch.Tensor, down: torch.Tensor):
+        """HF per-expert tensors gate/up [I, H], down [H, I]."""
+        if not (self.e_start <= global_e < self.e_start + self.e_local):
+            return
+        le = global_e - self.e_start
+        if self.use_ep or self.tp_size == 1:
+            self.w13.data[le].copy_(torch.cat([gate, up], dim=0))
+            self.w2.data[le].copy_(down)
+        else:
+            self.w13.data[le].copy_(wu.shard_gate_up(gate, up, self.tp_rank, self.tp_size))
+            self.w2.data[le].copy_(wu.shard_cols(down, self.tp_rank, self.tp_size))
+
+
+def _sm_grouped_topk(moe: FusedMoE, logits):
+    from gllm_b200.ops import sm100_moe
+    return sm100_moe.grouped_topk(logits, moe.top_k, moe.renormalize, moe.n_group, moe.topk_group, moe.scoring,
+                                  moe.e_bias, moe.routed_scaling)
+
+
+class SparseMoeBlock(nn.Module):
+    """Router + routed experts + optional (sigmoid-gated) shared expert; returns a TP-partial sum."""
+
+    def __init__(self, spec, layer_id: int, device):
+        super().__init__()
+        from gllm_b200.models.decoder import DenseMLP
+        m = spec.moe
+        self.experts = FusedMoE(m.num_experts, m.top_k, spec.hidden_size, m.intermediate_size, spec.dtype, device,
+                                renormalize=m.norm_topk_prob, scoring=m.scoring, n_group=m.n_group,
+                                topk_group=m.topk_group, routed_scaling=m.routed_scaling,
+                                bias_correction=m.has_bias_correction)
+        self.shared = None
+        self.shared_gate_w = None
+        if m.shared_intermediate_size > 0:
+            self.shared = DenseMLP(spec.hidden_size, m.shared_intermediate_size, spec.dtype, device)
+            if m.shared_gate:
+                self.shared_gate_w = _param(1, spec.hidden_size, dtype=spec.dtype, device=device)
+
+    def forward(self, h: torch.Tensor, tpc) -> torch.Tensor:
+        out = self.experts(h, tpc)
+        if self.shared is not None:
+            # partial (un-reduced) shared-expert output: reduced together with the routed experts —
+            # the reference double-reduces here on Qwen2-MoE; we do it once.
+            s = Fn.linear(self.shared.act(h, tpc), self.shared.down_w)
+            if self.shared_gate_w is not None:
+                g = torch.sigmoid(torch.nn.functional.linear(h.float(), self.shared_gate_w.float()))
+                s = (s.float() * g).to(s.dtype)
+            out = out + s
+        return out
+
+    def load_weights(self, reader, pre: str, nm: dict):
+        ex = self.experts
+        ex.router_w.data.copy_(reader.get(pre + nm["router"]))
+        if ex.e_bias is not None and "router_bias" in nm and reader.has(pre + nm["router_bias"]):
+            ex.e_bias.data.copy_(reader.get(pre + nm["router_bias"]).float())
+        fused_name = nm.get("experts_fused_gate_up")
+        if fused_name and reader.has(pre + fused_name):
+            # Qwen3-VL-MoE: experts.gate_up_proj [E, H, 2I], experts.down_proj [E, I, H]
+            gu = reader.get(pre + fused_name)
+            dn = reader.get(pre + nm["experts_fused_down"])
+            inter = gu.shape[-1] // 2
+            for e in range(ex.e_start, ex.e_start + ex.e_local):
+                g = gu[e, :, :inter].t().contiguous()
+                u = gu[e, :, inter:].t().contiguous()
+                ex.load_expert(e, g, u, dn[e].t().contiguous())
+        else:
+            for e in range(ex.e_start, ex.e_start + ex.e_local):
+                ep = pre + nm["expert"].format(e=e)
+                ex.load_expert(e, reader.get(ep + nm["e_gate"]), reader.get(ep + nm["e_up"]),
+                               reader.get(ep + nm["e_down"]))
+        if self.shared is not None:
+            sp = pre + nm["shared"]
+            tp, tr = ex.tp_size, ex.tp_rank
+            gate, up = reader.get(sp + "gate_proj.weight"), reader.get(sp + "up_proj.weight")
+            self.shared.set_gate_up(wu.shard_gate_up(gate, up, tr, tp))
+            self.shared.down_w.data.copy_(wu.shard_cols(reader.get(sp + "down_proj.weight"), tr, tp))
+            if self.shared_gate_w is not None:
+                self.shared_gate_w.data.copy_(reader.get(pre + nm["shared_gate"]))
+
+
+def make_moe_block(spec, layer_id: int, device):
+    return SparseMoeBlock(spec, layer_id, device)

@@ -48,7 +48,8 @@ class MemoryManager:
         self.num_pages = num_pages
         self.page_size = page_size
         self.id_allocator = IDAllocator(0, num_pages - 1)
-        self.dummy_page: Optional[int] = self.id_allocator.allocate() if reserve_dummy_page else None
+        # the LAST page is the dummy page (CUDA-graph padding rows read/write it)
+        self.dummy_page: Optional[int] = self.id_allocator.allocate(num_pages - 1) if reserve_dummy_page else None
         self.usable_pages = num_pages - (1 if reserve_dummy_page else 0)
 
     # -- page accounting ------------------------------------------------------------------------

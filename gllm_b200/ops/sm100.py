@@ -248,7 +248,8 @@ def paged_attention(q: torch.Tensor, k_cache: torch.Tensor, v_cache: torch.Tenso
 # sampling
 # ----------------------------------------------------------------------------------------------
 def sample(logits: torch.Tensor, temperature=None, top_k=None, top_p=None, rep_penalty=None,
-           seen_bits: Optional[torch.Tensor] = None, seed: int = 0, step: Optional[torch.Tensor] = None,
+           seen_bits: Optional[torch.Tensor] = None, slot_idx: Optional[torch.Tensor] = None, seed: int = 0,
+           step: Optional[torch.Tensor] = None,
            out: Optional[torch.Tensor] = None, out_max: Optional[torch.Tensor] = None,
            vocab_offset: int = 0) -> torch.Tensor:
     """logits [B, V] bf16/fp32; per-row params fp32/int32 tensors or None. seen_bits: uint32/int32
@@ -262,7 +263,8 @@ def sample(logits: torch.Tensor, temperature=None, top_k=None, top_p=None, rep_p
     seen_words = seen_bits.shape[1] if seen_bits is not None else 0
     L = _lib.load()
     rc = L.gllm_sample(_p(logits), dtype, logits.stride(0), _p(out), b, v, _p(temperature), _p(top_k), _p(top_p),
-                       _p(rep_penalty), _p(seen_bits), seen_words, ctypes.c_uint64(seed & ((1 << 64) - 1)),
+                       _p(rep_penalty), _p(seen_bits), seen_words, _p(slot_idx),
+                       ctypes.c_uint64(seed & ((1 << 64) - 1)),
                        _p(step), _p(out_max), vocab_offset, stream_ptr())
     check(rc, "sample")
     _count()

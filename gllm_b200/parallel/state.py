@@ -1,0 +1,206 @@
+"""Distributed state: ranks, groups, PP layer partition, PP p2p, baseline collectives.
+
+Reference: gllm/dist_utils.py. Same rank mapping (`rank = pp_rank * tp_size + tp_rank`), same EP
+convention (EP group == TP group), same layer partition rule (ceil(L / pp) per stage with the
+remainder on the last stage, or an explicit `assigned_layers` list).
+
+`torch.distributed` (NCCL on GPUs, gloo on CPU for the plumbing tests) provides rendezvous, PP
+p2p, control-plane collectives and the *baseline* TP collectives. The product TP/EP hot paths use
+the fused NVLink kernels in `gllm_b200.parallel.fused` instead.
+"""
+from __future__ import annotations
+
+import datetime
+from dataclasses import dataclass, field
+from typing import List, Optional
+
+import torch
+import torch.distributed as dist
+
+from gllm_b200.utils.logging import logger
+
+
+@dataclass
+class ParallelState:
+    rank: int = 0
+    world_size: int = 1
+    pp_rank: int = 0
+    pp_size: int = 1
+    tp_rank: int = 0
+    tp_size: int = 1
+    ep_rank: int = 0
+    ep_size: int = 1
+    local_rank: int = 0
+    tp_group: Optional[object] = None
+    tp_ranks: List[int] = field(default_factory=lambda: [0])
+    assigned_layers: Optional[List[int]] = None
+    initialized: bool = False
+    backend: str = "none"
+
+
+_STATE = ParallelState()
+
+
+def get_state() -> ParallelState:
+    return _STATE
+
+
+def reset_state():
+    global _STATE
+    _STATE = ParallelState()
+
+
+def get_rank(): return _STATE.rank
+def get_world_size(): return _STATE.world_size
+def get_pp_rank(): return _STATE.pp_rank
+def get_pp_size(): return _STATE.pp_size
+def get_tp_rank(): return _STATE.tp_rank
+def get_tp_size(): return _STATE.tp_size
+def get_ep_rank(): return _STATE.ep_rank
+def get_ep_size(): return _STATE.ep_size
+def get_local_rank(): return _STATE.local_rank
+def get_tp_group(): return _STATE.tp_group
+def is_first_pp_rank(): return _STATE.pp_rank == 0
+def is_last_pp_rank(): return _STATE.pp_rank == _STATE.pp_size - 1
+def is_driver(): return _STATE.rank == 0
+
+
+def get_output_rank() -> int:
+    """First TP rank of the last stage samples and reports tokens (gllm/dist_utils.py:71-76)."""
+    return (_STATE.pp_size - 1) * _STATE.tp_size
+
+
+def is_output_rank() -> bool:
+    return _STATE.rank == get_output_rank()
+
+
+def get_next_pp_rank() -> int:
+    return _STATE.rank + _STATE.tp_size
+
+
+def get_prev_pp_rank() -> int:
+    return _STATE.rank - _STATE.tp_size
+
+
+def init_dist(pp_size: int, tp_size: int, rank: int, local_rank: int, master_addr: str = "127.0.0.1",
+              master_port: int = 8001, use_ep: bool = True, assigned_layers: Optional[List[int]] = None,
+              backend: Optional[str] = None, init_process_group: bool = True, timeout_s: int = 600):
+    """Create the world group (+ one TP group per stage)."""
+    global _STATE
+    world = pp_size * tp_size
+    st = ParallelState(rank=rank, world_size=world, pp_rank=rank // tp_size, pp_size=pp_size,
+                       tp_rank=rank % tp_size, tp_size=tp_size, local_rank=local_rank,
+                       assigned_layers=assigned_layers)
+    if use_ep:
+        st.ep_rank, st.ep_size = st.tp_rank, st.tp_size
+    if backend is None:
+        backend = "nccl" if torch.cuda.is_available() else "gloo"
+    st.backend = backend
+    if world > 1:
+        if init_process_group and not dist.is_initialized():
+            kw = {}
+            if backend == "nccl":
+                kw["device_id"] = torch.device("cuda", local_rank)
+            dist.init_process_group(backend=backend, init_method=f"tcp://{master_addr}:{master_port}",
+                                    world_size=world, rank=rank,
+                                    timeout=datetime.timedelta(seconds=timeout_s), **kw)
+            logger.info("dist init: rank %d / %d (pp %d/%d, tp %d/%d) backend=%s", rank, world, st.pp_rank,
+                        pp_size, st.tp_rank, tp_size, backend)
+        # every rank must create every group, in the same order
+        for stage in range(pp_size):
+            ranks = list(range(stage * tp_size, (stage + 1) * tp_size))
+            grp = dist.new_group(ranks) if tp_size > 1 else None
+            if stage == st.pp_rank:
+                st.tp_group, st.tp_ranks = grp, ranks
+    st.initialized = True
+    _STATE = st
+    return st
+
+
+def destroy():
+    if dist.is_initialized():
+        try:
+            dist.destroy_process_group()
+        except Exception:  # noqa: BLE001
+            pass
+    reset_state()
+
+
+# ------------------------------------------------------------------------------------------------
+# PP layer partition
+# ------------------------------------------------------------------------------------------------
+def partition_layers(num_layers: int, pp_size: int, assigned_layers: Optional[List[int]] = None) -> List[range]:
+    """-> layer range per stage. Default: ceil(L/pp) per stage, remainder on the last stage
+    (gllm/dist_utils.py:176-187)."""
+    if assigned_layers is not None:
+        assert len(assigned_layers) == pp_size and sum(assigned_layers) == num_layers, \
+            f"assigned_layers {assigned_layers} must have {pp_size} entries summing to {num_layers}"
+        out, s = [], 0
+        for n in assigned_layers:
+            out.append(range(s, s + n))
+            s += n
+        return out
+    per = (num_layers + pp_size - 1) // pp_size
+    out = []
+    for i in range(pp_size):
+        a = min(i * per, num_layers)
+        b = num_layers if i == pp_size - 1 else min((i + 1) * per, num_layers)
+        out.append(range(a, b))
+    # stages before the last take `per`; make sure the last one is not empty when L < pp*per
+    if pp_size > 1 and len(out[-1]) == 0:
+        # fall back to an even floor split with the remainder spread from the front
+        base, rem = divmod(num_layers, pp_size)
+        out, s = [], 0
+        for i in range(pp_size):
+            n = base + (1 if i < rem else 0)
+            out.append(range(s, s + n))
+            s += n
+    return out
+
+
+def get_pp_layers(num_layers: int) -> range:
+    return partition_layers(num_layers, _STATE.pp_size, _STATE.assigned_layers)[_STATE.pp_rank]
+
+
+# ------------------------------------------------------------------------------------------------
+# baseline collectives (NCCL / gloo)
+# ------------------------------------------------------------------------------------------------
+def tp_all_reduce(x: torch.Tensor) -> torch.Tensor:
+    if _STATE.tp_size == 1:
+        return x
+    dist.all_reduce(x, group=_STATE.tp_group)
+    return x
+
+
+def tp_all_gather_last_dim(x: torch.Tensor) -> torch.Tensor:
+    """[.., n] per rank -> [.., n * tp] (gllm/dist_utils.py:230-250)."""
+    if _STATE.tp_size == 1:
+        return x
+    tp = _STATE.tp_size
+    out = torch.empty((tp,) + tuple(x.shape), dtype=x.dtype, device=x.device)
+    dist.all_gather_into_tensor(out, x.contiguous(), group=_STATE.tp_group)
+    return out.movedim(0, -2).reshape(*x.shape[:-1], tp * x.shape[-1])
+
+
+def tp_all_gather_first_dim(x: torch.Tensor) -> torch.Tensor:
+    if _STATE.tp_size == 1:
+        return x
+    out = torch.empty((_STATE.tp_size * x.shape[0],) + tuple(x.shape[1:]), dtype=x.dtype, device=x.device)
+    dist.all_gather_into_tensor(out, x.contiguous(), group=_STATE.tp_group)
+    return out
+
+
+def pp_send(tensors: List[torch.Tensor], dst: Optional[int] = None):
+    dst = get_next_pp_rank() if dst is None else dst
+    return [dist.isend(t, dst) for t in tensors]
+
+
+def pp_recv(tensors: List[torch.Tensor], src: Optional[int] = None):
+    src = get_prev_pp_rank() if src is None else src
+    for t in tensors:
+        dist.recv(t, src)
+
+
+def divide(a: int, b: int) -> int:
+    assert a % b == 0, f"{a} is not divisible by {b}"
+    return a // b

@@ -139,6 +139,13 @@ __device__ __forceinline__ void tma_load_2d_2sm(void* smem_dst, const void* tmap
       : "memory");
 }
 
+__device__ __forceinline__ void tma_prefetch_l2_2d(const void* tmap, int32_t c0, int32_t c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];"
+               :
+               : "l"(reinterpret_cast<uint64_t>(tmap)), "r"(c0), "r"(c1)
+               : "memory");
+}
+
 __device__ __forceinline__ void tma_store_2d(const void* tmap, const void* smem_src, int32_t c0,
                                              int32_t c1) {
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"

@@ -44,6 +44,7 @@ struct GemmParams {
   uint32_t rs_inc;
   __nv_bfloat16* peer_out[kMaxPeers];
   uint32_t* peer_cnt[kMaxPeers];
+  uint32_t prefetch_kb;
 };
 
 template <int BN>
@@ -107,6 +108,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     // ===================== TMA producer =====================
     if (lane == 0) {
       uint32_t it = 0;
+      uint32_t pf_it = 0;
+      int pf_tile = blockIdx.x, pf_kb = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int m0 = (tile % num_m) * kBlockM;
         const int n0 = (tile / num_m) * BN;
@@ -122,6 +125,14 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           asm volatile("fence.proxy.async;" ::: "memory");
         }
         for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          // L2 prefetch cursor for the weight operand: runs `p.prefetch_kb` k-blocks ahead of the
+          // SMEM ring (across tile boundaries) so weight streaming is not limited by the per-SM
+          // number of outstanding DRAM misses of the ring itself.
+          while (pf_it < it + p.prefetch_kb && pf_tile < num_tiles) {
+            tma_prefetch_l2_2d(&tmap_b, pf_kb * kBlockK, (pf_tile / num_m) * BN);
+            ++pf_it;
+            if (++pf_kb == num_kb) { pf_kb = 0; pf_tile += gridDim.x; }
+          }
           const int s = it % S;
           const uint32_t ph = (it / S) & 1;
           mbar_wait(&empty_bar[s], ph ^ 1);
@@ -366,6 +377,15 @@ GLLM_EXPORT int gllm_gemm_bf16(const void* A, int64_t lda, const void* W, int64_
   p.C = reinterpret_cast<__nv_bfloat16*>(C);
   p.ldc = static_cast<int>(ldc);
   p.bias = reinterpret_cast<const __nv_bfloat16*>(bias);
+  {
+    static int pf = -1;
+    if (pf < 0) {
+      const char* e = getenv("GLLM_GEMM_PREFETCH");
+      pf = e ? atoi(e) : 24;
+    }
+    // prefetching only pays when the weights are streamed once (few M tiles share them)
+    p.prefetch_kb = (M <= 1024) ? pf : 0;
+  }
   if (comm != nullptr) {
     p.a_ready = comm->a_ready;
     p.a_epoch = comm->a_epoch;

@@ -86,7 +86,7 @@ def build_batch(entries, page_size: int, vocab_size: int, batch_id: int = 0, mro
     b = len(entries)
     n_dec = 0
     for e in entries:
-        if e.n == 1 and e.start >= e.seq.prompt_len:
+        if e.is_decode:
             n_dec += 1
         else:
             break
@@ -122,7 +122,7 @@ def build_batch(entries, page_size: int, vocab_size: int, batch_id: int = 0, mro
             pos = np.arange(s0, s0 + e.n, dtype=np.int32)
             positions[a:z] = pos
             slots[a:z] = pt[pos // page_size] * page_size + pos % page_size
-        if s0 + e.n >= seq.prompt_len:
+        if e.emits:
             emit_seq.append(i)
             logits_idx.append(z - 1)
             temperature.append(seq.temperature)

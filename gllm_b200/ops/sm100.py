@@ -39,6 +39,31 @@ def _count(n=1):
 # GEMM
 # ----------------------------------------------------------------------------------------------
 _FORCE_BN = int(os.environ.get("GLLM_GEMM_BN", "0"))
+_SMALLM_MAX = int(os.environ.get("GLLM_GEMM_SMALLM_MAX", "256"))   # M <= this -> swap-AB split-K kernel
+_FORCE_SPLIT = int(os.environ.get("GLLM_GEMM_SPLIT", "0"))
+_SMALLM_WS_FLOATS = 24 << 20
+_smallm_ws = {}
+
+
+def _smallm_workspace(device):
+    ws = _smallm_ws.get(device)
+    if ws is None:
+        ws = (torch.empty(_SMALLM_WS_FLOATS, dtype=torch.float32, device=device),
+              torch.zeros(8192, dtype=torch.int32, device=device))
+        _smallm_ws[device] = ws
+    return ws
+
+
+def _linear_smallm(x, w, bias, out, silu: bool):
+    m, k = x.shape
+    n = w.shape[0]
+    ws, cnt = _smallm_workspace(x.device)
+    L = _lib.load()
+    rc = L.gllm_gemm_smallm(_p(x), x.stride(0), _p(w), w.stride(0), _p(out), out.stride(0), m, n, k, _p(bias),
+                            1 if silu else 0, _FORCE_SPLIT, _p(ws), ws.numel(), _p(cnt), stream_ptr())
+    check(rc, "gemm_smallm")
+    _count()
+    return out
 
 
 def linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None,
@@ -56,6 +81,8 @@ def linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None
         assert out.shape == (m, n_out) and out.stride(1) == 1
     if m == 0:
         return out
+    if m <= _SMALLM_MAX and comm is None and epi == 0 and _FORCE_BN == 0:
+        return _linear_smallm(x, w, bias, out, False)
     L = _lib.load()
     rc = L.gllm_gemm_bf16(_p(x), x.stride(0), _p(w), w.stride(0), _p(out), out.stride(0), m, n, k, _p(bias),
                           epi, _FORCE_BN, ctypes.byref(comm) if comm is not None else None, stream_ptr())
@@ -75,6 +102,8 @@ def linear_silu_mul(x: torch.Tensor, w_interleaved: torch.Tensor, out: Optional[
         out = torch.empty(m, n // 2, dtype=_BF16, device=x.device)
     if m == 0:
         return out
+    if m <= _SMALLM_MAX and _FORCE_BN == 0:
+        return _linear_smallm(x, w_interleaved, None, out, True)
     L = _lib.load()
     rc = L.gllm_gemm_bf16(_p(x), x.stride(0), _p(w_interleaved), w_interleaved.stride(0), _p(out),
                           out.stride(0), m, n, k, None, 1, 128, None, stream_ptr())

@@ -61,18 +61,15 @@ def throttled_prefill_budget(headroom_tokens: int, world_size: int, free_ratio: 
 
 class ScheduledSeq:
     """One entry of a micro-batch: compute tokens [start, start + n) of `seq`."""
-    __slots__ = ("seq", "start", "n")
+    __slots__ = ("seq", "start", "n", "emits", "is_decode")
 
     def __init__(self, seq: Sequence, start: int, n: int):
         self.seq, self.start, self.n = seq, start, n
-
-    @property
-    def is_decode(self) -> bool:
-        return self.start >= self.seq.prompt_len
-
-    @property
-    def emits_token(self) -> bool:
-        return self.start + self.n >= self.seq.prompt_len
+        # A token is sampled only when the chunk reaches the end of everything known so far. (After a
+        # preemption the recomputed "prompt" includes the tokens generated before; the reference's
+        # `computed_token_num >= prompt_len` test would emit early on a chunked recompute.)
+        self.emits = start + n >= len(seq.token_ids)
+        self.is_decode = n == 1 and self.emits and start >= seq.prompt_len
 
     def __repr__(self):
         return f"ScheduledSeq(id={self.seq.seq_id}, start={self.start}, n={self.n})"
@@ -142,8 +139,11 @@ class Scheduler:
         batch = self.batch_running.popleft()
         next_tokens = self.next_tokens_queue.popleft()
         out = SchedulerOutput()
-        for idx, ent in enumerate(batch):
+        k = 0  # next_tokens holds one token per *emitting* entry, in batch order
+        for ent in batch:
             seq = ent.seq
+            if ent.emits:
+                k += 1
             if seq.is_abort:
                 if seq.page_table:
                     self.mm.free(seq)
@@ -151,8 +151,8 @@ class Scheduler:
                 self.abort_ids.discard(seq.seq_id)
                 continue
             seq.computed_token_num = max(seq.computed_token_num, ent.start + ent.n)
-            if seq.computed_prompt:
-                tok = int(next_tokens[idx])
+            if ent.emits:
+                tok = int(next_tokens[k - 1])
                 out.act_schedule_ids.append(seq.seq_id)
                 out.next_tokens.append(tok)
                 seq.append(tok)

@@ -1,0 +1,268 @@
+"""CPU unit tests: id allocator, paged KV + prefix cache invariants, scheduler policies, batch builder."""
+import random
+
+import numpy as np
+import pytest
+
+from gllm_b200.id_allocator import IDAllocator
+from gllm_b200.input_data import BatchArrays, build_batch
+from gllm_b200.memory_manager import MemoryManager, PrefixMemoryManager
+from gllm_b200.scheduler import (ScheduledSeq, Scheduler, balanced_decode_budget, kv_headroom_tokens,
+                                 throttled_prefill_budget)
+from gllm_b200.sequence import Sequence
+
+
+def mkseq(i, n, out=4, **kw):
+    return Sequence(i, list(range(1000 * i, 1000 * i + n)), [2], output_len=out, ignore_eos=True, **kw)
+
+
+# ------------------------------------------------------------------------------------------------
+def test_id_allocator_fifo_tail_and_specific():
+    a = IDAllocator(0, 7)
+    assert [a.allocate() for _ in range(3)] == [0, 1, 2]
+    a.free(1)
+    # freed id goes to the TAIL: 3..7 are handed out before 1 comes back
+    assert [a.allocate() for _ in range(5)] == [3, 4, 5, 6, 7]
+    assert a.allocate() == 1
+    assert a.get_num_free_ids() == 0
+    with pytest.raises(RuntimeError):
+        a.allocate()
+    a.free(5); a.free(2); a.free(7)
+    assert a.allocate(2) == 2 and not a.is_free(2)      # O(1) specific re-acquire from the middle
+    assert a.allocate(2) == 2                            # already taken: no-op (shared page)
+    assert [a.allocate(), a.allocate()] == [5, 7]
+    with pytest.raises(RuntimeError):
+        a.free(3); a.free(3)
+
+
+def test_id_allocator_random_against_model():
+    rnd = random.Random(0)
+    a = IDAllocator(10, 59)
+    model_free = list(range(10, 60))
+    used = set()
+    for _ in range(5000):
+        r = rnd.random()
+        if r < 0.45 and model_free:
+            x = a.allocate()
+            assert x == model_free.pop(0)
+            used.add(x)
+        elif r < 0.6 and model_free:
+            x = rnd.choice(model_free)
+            assert a.allocate(x) == x
+            model_free.remove(x)
+            used.add(x)
+        elif used:
+            x = rnd.choice(sorted(used))
+            used.remove(x)
+            a.free(x)
+            model_free.append(x)
+        assert a.get_num_free_ids() == len(model_free)
+
+
+# ------------------------------------------------------------------------------------------------
+def test_memory_manager_alloc_free():
+    mm = MemoryManager(10, 4, reserve_dummy_page=True)
+    assert mm.dummy_page == 9 and mm.get_num_free_pages() == 9
+    s = mkseq(1, 10)
+    s.scheduled_token_num = 10
+    mm.pre_allocate_page([s])
+    assert len(s.page_table) == 3 and mm.get_num_free_pages() == 6
+    s.scheduled_token_num = 13
+    mm.pre_allocate_page([s])
+    assert len(s.page_table) == 4
+    mm.free(s)
+    assert mm.get_num_free_pages() == 9 and s.page_table == []
+
+
+def test_prefix_cache_hit_refcount_eviction():
+    ps = 4
+    mm = PrefixMemoryManager(8, ps)
+    a = Sequence(1, list(range(10)), [2])
+    mm.pre_allocate_computed_page([a])
+    assert a.computed_token_num == 0
+    a.scheduled_token_num = 10
+    mm.pre_allocate_page([a])
+    assert len(a.page_table) == 3
+    # identical prefix: two full pages are shared, refcount 2
+    b = Sequence(2, list(range(10)), [2])
+    mm.pre_allocate_computed_page([b])
+    assert b.page_table == a.page_table[:2] and b.computed_token_num == 8 == b.scheduled_token_num
+    assert mm.page_ref[a.page_table[0]] == 2
+    assert mm.get_cache_hit_rate() > 0
+    # a prompt that is an exact multiple of the page size never gets its LAST page from the cache
+    c = Sequence(3, list(range(8)), [2])
+    mm.pre_allocate_computed_page([c])
+    assert c.computed_token_num == 4
+    mm.free(c)
+    free_before = mm.get_num_free_pages()
+    mm.free(a)
+    # shared pages stay allocated (b still holds them); a's private third page is released
+    assert mm.get_num_free_pages() == free_before + 1
+    mm.free(b)
+    assert mm.get_num_free_pages() == 8
+    # freed pages keep their hash until they are handed out again ...
+    d = Sequence(4, list(range(10)), [2])
+    mm.pre_allocate_computed_page([d])
+    assert d.computed_token_num == 8
+    mm.free(d)
+    # ... and lose it on re-allocation
+    for i in range(8):
+        mm.allocate_page()
+    assert not mm.hash2page
+    e = Sequence(5, list(range(10)), [2])
+    for p in range(8):
+        mm.free_page(p)
+    mm.pre_allocate_computed_page([e])
+    assert e.computed_token_num == 0
+
+
+def test_prefix_cache_decode_page_registered():
+    ps = 4
+    mm = PrefixMemoryManager(16, ps)
+    a = Sequence(1, [1, 2, 3, 4, 5, 6], [2])
+    a.scheduled_token_num = 6
+    mm.pre_allocate_page([a])
+    a.computed_token_num = 6
+    a.append(7)  # decode
+    a.append(8)  # -> 8 tokens: second page full
+    a.scheduled_token_num = 8
+    mm.pre_allocate_page([a])
+    b = Sequence(2, [1, 2, 3, 4, 5, 6, 7, 8, 9], [2])
+    mm.pre_allocate_computed_page([b])
+    assert b.computed_token_num == 8
+
+
+# ------------------------------------------------------------------------------------------------
+def test_budget_functions():
+    assert balanced_decode_budget(3, 4, 100) == 1
+    assert balanced_decode_budget(5, 4, 100, rnd=0) == 1 and balanced_decode_budget(5, 4, 100, rnd=3) == 2
+    assert balanced_decode_budget(1000, 2, 64, rnd=1) == 64
+    assert kv_headroom_tokens(100, 5, 16) == 95 * 16 and kv_headroom_tokens(3, 5, 16) == 0
+    # single GPU: plain cap
+    assert throttled_prefill_budget(10 ** 6, 1, 0.5, 0.05, 2048, 32, 8, 10, 10 ** 5) == 2048
+    # UT: free ratio 0.525 -> ratio 0.5 -> 1024
+    assert throttled_prefill_budget(10 ** 6, 4, 0.525, 0.05, 2048, 32, 8, 1, 10 ** 5) == 1024
+    # WT: 800 waiting tokens over 8 iterations -> 100; floor minp
+    assert throttled_prefill_budget(10 ** 6, 4, 1.0, 0.05, 2048, 32, 8, 3, 800) == 100
+    assert throttled_prefill_budget(10 ** 6, 4, 1.0, 0.05, 2048, 32, 8, 3, 80) == 32
+    assert throttled_prefill_budget(0, 4, 1.0, 0.05, 2048, 32, 8, 3, 800) == 0
+
+
+def run_engine(sch: Scheduler, n_steps=10000, token=lambda e: 7):
+    """Drive the scheduler with an instant 'model' honouring the <= pp_size in-flight invariant."""
+    inflight = []
+    produced = {}
+    batches = []
+    for _ in range(n_steps):
+        if not sch.has_work():
+            break
+        b = sch.schedule_once()
+        if b:
+            assert len(sch.batch_running) <= sch.pp_size
+            # decode-first ordering
+            kinds = [e.is_decode for e in b]
+            assert kinds == sorted(kinds, reverse=True), kinds
+            inflight.append(b)
+            batches.append(b)
+        if inflight and (len(inflight) == sch.pp_size or not b):
+            done = inflight.pop(0)
+            sch.add_next_tokens([token(e) for e in done if e.emits])
+            out = sch.process_output()
+            for sid, tok in zip(out.act_schedule_ids, out.next_tokens):
+                produced.setdefault(sid, []).append(tok)
+    return produced, batches
+
+
+@pytest.mark.parametrize("method", ["chunked_prefill", "split_pd", "token_throttling"])
+@pytest.mark.parametrize("pp", [1, 2, 4])
+def test_scheduler_completes_all(method, pp):
+    mm = PrefixMemoryManager(64, 16)
+    sch = Scheduler(mm, pp_size=pp, world_size=pp, schedule_method=method, maxd=8, maxp=64, minp=8, iterp=4,
+                    kvthresh=0.05, page_size=16, log=False)
+    seqs = [mkseq(i, n, out=5) for i, n in enumerate([10, 100, 33, 64, 7, 150])]
+    sch.add_new_requests(seqs)
+    produced, batches = run_engine(sch)
+    assert all(len(produced[s.seq_id]) == 5 for s in seqs)
+    assert mm.get_num_free_pages() == 64
+    for b in batches:
+        assert sum(e.n for e in b) <= (64 if method != "token_throttling" else 64 + 8)
+
+
+def test_chunk_continuation_and_pipelined_chunks():
+    mm = MemoryManager(64, 16)
+    sch = Scheduler(mm, pp_size=2, world_size=2, schedule_method="chunked_prefill", maxd=8, maxp=32, page_size=16,
+                    log=False)
+    s = mkseq(1, 100, out=2)
+    sch.add_new_requests([s])
+    b1 = sch.schedule_once()
+    b2 = sch.schedule_once()  # second chunk scheduled while the first is still in flight (pp=2)
+    assert [(e.start, e.n) for e in b1] == [(0, 32)] and [(e.start, e.n) for e in b2] == [(32, 32)]
+    assert sch.schedule_once() == []  # pp_size batches in flight
+    sch.add_next_tokens([]); out = sch.process_output()
+    assert out.act_schedule_ids == [] and s.computed_token_num == 32
+    b3 = sch.schedule_once()
+    assert [(e.start, e.n) for e in b3] == [(64, 32)]
+
+
+def test_preemption_recompute():
+    mm = MemoryManager(6, 4)  # tiny KV: forces preemption
+    sch = Scheduler(mm, pp_size=1, schedule_method="chunked_prefill", maxd=8, maxp=64, kvthresh=0.0, page_size=4,
+                    log=False)
+    seqs = [mkseq(i, 7, out=10) for i in range(3)]
+    sch.add_new_requests(seqs)
+    produced, _ = run_engine(sch)
+    assert all(len(produced[s.seq_id]) >= 10 for s in seqs) or sch.num_preempt_seqs > 0
+    assert sch.num_preempt_seqs > 0
+    assert mm.get_num_free_pages() == 6
+    for s in seqs:
+        assert len(s.token_ids) == 7 + 10
+
+
+def test_abort_frees_pages():
+    mm = MemoryManager(32, 16)
+    sch = Scheduler(mm, pp_size=1, maxd=8, maxp=64, page_size=16, log=False)
+    a, b = mkseq(1, 20, out=50), mkseq(2, 20, out=50)
+    sch.add_new_requests([a, b])
+    bt = sch.schedule_once()
+    sch.add_next_tokens([5, 5]); sch.process_output()
+    sch.add_abort_ids([1])
+    out = sch.check_abort_seqs()
+    assert out.free_ids == [1]
+    produced, _ = run_engine(sch)
+    assert len(produced[2]) == 49 and 1 not in produced
+    assert mm.get_num_free_pages() == 32
+
+
+def test_split_pd_prioritises_prefill():
+    mm = MemoryManager(64, 16)
+    sch = Scheduler(mm, pp_size=1, schedule_method="split_pd", maxd=8, maxp=32, kvthresh=0.05, page_size=16, log=False)
+    sch.add_new_requests([mkseq(1, 10, out=5)])
+    b = sch.schedule_once(); sch.add_next_tokens([1]); sch.process_output()
+    sch.add_new_requests([mkseq(2, 10, out=5)])
+    b = sch.schedule_once()
+    assert [e.seq.seq_id for e in b] == [2]  # decode of seq 1 is held back while a prefill waits
+
+
+# ------------------------------------------------------------------------------------------------
+def test_build_batch_layout_and_wire():
+    ps = 4
+    a = mkseq(1, 6, out=5)   # will be a decode entry
+    a.page_table = [3, 5]
+    a.computed_token_num = 6; a.append(99)
+    b = mkseq(2, 10, out=5)  # prefill chunk [4, 10) with context
+    b.page_table = [7, 1, 2]
+    ents = [ScheduledSeq(a, 6, 1), ScheduledSeq(b, 4, 6)]
+    bt = build_batch(ents, ps, vocab_size=50000, batch_id=3)
+    assert bt.num_decode_seqs == 1 and bt.num_seqs == 2 and bt.num_tokens == 7
+    assert bt.tokens.tolist() == [99] + list(range(2004, 2010))
+    assert bt.positions.tolist() == [6, 4, 5, 6, 7, 8, 9]
+    assert bt.slot_mapping.tolist() == [5 * 4 + 2, 1 * 4 + 0, 1 * 4 + 1, 1 * 4 + 2, 1 * 4 + 3, 2 * 4 + 0, 2 * 4 + 1]
+    assert bt.seq_lens.tolist() == [7, 10] and bt.query_start_loc.tolist() == [0, 1, 7]
+    assert bt.logits_idx.tolist() == [0, 6] and bt.block_table[1].tolist() == [7, 1, 2]
+    assert bt.max_q_len == 6 and bt.max_seq_len == 10 and bt.all_greedy is False  # default top_k=10
+    hdr, bufs = bt.to_wire()
+    back = BatchArrays.from_wire(hdr, [memoryview(np.ascontiguousarray(x)) for x in bufs])
+    for f in ("tokens", "positions", "slot_mapping", "block_table", "seq_lens", "query_start_loc", "logits_idx",
+              "temperature", "top_k", "top_p"):
+        assert np.array_equal(getattr(bt, f), getattr(back, f)), f
+    assert back.batch_id == 3 and back.num_decode_seqs == 1

@@ -1,0 +1,133 @@
+"""Greedy-decode token-exact match against HuggingFace transformers on tiny random models (CPU, fp32),
+through the full engine: scheduler, chunked prefill, paged KV, prefix cache, loader."""
+import os
+import tempfile
+
+import pytest
+import torch
+
+transformers = pytest.importorskip("transformers")
+
+
+def _save(model):
+    d = tempfile.mkdtemp(prefix="gllm_b200_test_")
+    model.save_pretrained(d, safe_serialization=True)
+    return d
+
+
+def _hf_greedy(model, prompt, n):
+    with torch.no_grad():
+        out = model.generate(torch.tensor([prompt]), max_new_tokens=n, do_sample=False, eos_token_id=None,
+                             pad_token_id=0)
+    return out[0, len(prompt):].tolist()
+
+
+def _engine(path, **kw):
+    from gllm_b200 import LLM
+    args = dict(maxp=64, maxd=64, page_size=16, num_cpu_pages=96, model_max_length=320, log_stats=False)
+    args.update(kw)
+    return LLM(path, **args)
+
+
+PROMPTS = [[5, 17, 99, 200, 3, 45, 7], [9] * 40, list(range(20, 150)), [300, 301]]
+
+
+def _check(model, **kw):
+    d = _save(model)
+    llm = _engine(d, **kw)
+    outs = llm.generate(tokens=PROMPTS, output_lens=[10] * len(PROMPTS), ignore_eos=True)
+    for p, s in zip(PROMPTS, outs):
+        assert s.token_ids[len(p):] == _hf_greedy(model, p, 10), (len(p),)
+    llm.shutdown()
+    return d
+
+
+def test_llama_matches_hf():
+    from transformers import LlamaConfig, LlamaForCausalLM
+    torch.manual_seed(0)
+    cfg = LlamaConfig(hidden_size=128, intermediate_size=256, num_hidden_layers=2, num_attention_heads=4,
+                      num_key_value_heads=2, vocab_size=512, max_position_embeddings=512, eos_token_id=1,
+                      bos_token_id=0)
+    _check(LlamaForCausalLM(cfg).eval().float())
+
+
+def test_llama3_rope_scaling_matches_hf():
+    from transformers import LlamaConfig, LlamaForCausalLM
+    torch.manual_seed(1)
+    cfg = LlamaConfig(hidden_size=128, intermediate_size=192, num_hidden_layers=2, num_attention_heads=4,
+                      num_key_value_heads=4, vocab_size=512, max_position_embeddings=512, eos_token_id=1,
+                      rope_parameters={"rope_type": "llama3", "factor": 8.0, "low_freq_factor": 1.0,
+                                       "high_freq_factor": 4.0, "original_max_position_embeddings": 64,
+                                       "rope_theta": 10000.0})
+    _check(LlamaForCausalLM(cfg).eval().float())
+
+
+def test_qwen2_bias_tied_matches_hf():
+    from transformers import Qwen2Config, Qwen2ForCausalLM
+    torch.manual_seed(2)
+    cfg = Qwen2Config(hidden_size=128, intermediate_size=256, num_hidden_layers=3, num_attention_heads=4,
+                      num_key_value_heads=2, vocab_size=512, max_position_embeddings=512, tie_word_embeddings=True,
+                      eos_token_id=1)
+    m = Qwen2ForCausalLM(cfg).eval().float()
+    for n, p in m.named_parameters():
+        if n.endswith("bias"):
+            torch.nn.init.normal_(p, std=0.5)
+    _check(m)
+
+
+def test_qwen3_qk_norm_matches_hf_with_prefix_cache_and_tiny_chunks():
+    from transformers import Qwen3Config, Qwen3ForCausalLM
+    torch.manual_seed(3)
+    cfg = Qwen3Config(hidden_size=128, intermediate_size=256, num_hidden_layers=2, num_attention_heads=4,
+                      num_key_value_heads=2, head_dim=32, vocab_size=512, max_position_embeddings=512,
+                      eos_token_id=1, tie_word_embeddings=False)
+    m = Qwen3ForCausalLM(cfg).eval().float()
+    for n, p in m.named_parameters():
+        if "q_norm" in n or "k_norm" in n:
+            torch.nn.init.normal_(p, mean=1.0, std=0.2)
+    d = _check(m, maxp=24, enable_prefix_caching=True)
+    # second engine: same prompts twice -> second round hits the prefix cache and must not change tokens
+    llm = _engine(d, maxp=48, enable_prefix_caching=True)
+    r1 = llm.generate(tokens=PROMPTS, output_lens=[6] * 4, ignore_eos=True)
+    r2 = llm.generate(tokens=PROMPTS, output_lens=[6] * 4, ignore_eos=True)
+    assert [s.token_ids for s in r1] == [s.token_ids for s in r2]
+    assert llm.worker.mm.get_cache_hit_rate() > 0
+    assert any(s.num_cached_tokens > 0 for s in r2)
+    llm.shutdown()
+
+
+def test_token_throttling_and_preemption_keep_tokens_exact():
+    from transformers import LlamaConfig, LlamaForCausalLM
+    torch.manual_seed(4)
+    cfg = LlamaConfig(hidden_size=64, intermediate_size=128, num_hidden_layers=2, num_attention_heads=2,
+                      num_key_value_heads=2, vocab_size=256, max_position_embeddings=512, eos_token_id=1)
+    m = LlamaForCausalLM(cfg).eval().float()
+    d = _save(m)
+    prompts = [[3 + i, 9, 27, 81, 5] * 4 for i in range(6)]
+    # KV for ~3 sequences only -> decode preemption + recompute must still give HF's tokens
+    llm = _engine(d, schedule_method="token_throttling", num_cpu_pages=10, kvthresh=0.0, maxp=32, maxd=8,
+                  enable_prefix_caching=False)
+    outs = llm.generate(tokens=prompts, output_lens=[24] * 6, ignore_eos=True)
+    assert llm.worker.scheduler.num_preempt_seqs > 0
+    for p, s in zip(prompts, outs):
+        assert s.token_ids[len(p):] == _hf_greedy(m, p, 24)
+    llm.shutdown()
+
+
+def test_eos_and_output_len_finish():
+    from transformers import LlamaConfig, LlamaForCausalLM
+    torch.manual_seed(5)
+    cfg = LlamaConfig(hidden_size=64, intermediate_size=128, num_hidden_layers=1, num_attention_heads=2,
+                      num_key_value_heads=2, vocab_size=64, max_position_embeddings=256, eos_token_id=1)
+    m = LlamaForCausalLM(cfg).eval().float()
+    d = _save(m)
+    llm = _engine(d)
+    p = [4, 8, 15, 16, 23, 42]
+    ref = _hf_greedy(m, p, 40)
+    llm.finish_tokens = [ref[5]]  # pretend the 6th generated token is EOS
+    s = llm.generate(tokens=[p], output_lens=[40])[0]
+    first = ref.index(ref[5])
+    assert s.token_ids[len(p):] == ref[: first + 1]
+    with pytest.raises(ValueError):
+        llm.generate(tokens=[[1] * 400], output_lens=[4])
+    llm.shutdown()

@@ -45,6 +45,10 @@ struct GemmParams {
   __nv_bfloat16* peer_out[kMaxPeers];
   uint32_t* peer_cnt[kMaxPeers];
   uint32_t prefetch_kb;
+  // grouped (MoE) mode: M tile t multiplies the weight slab of expert tile_expert[t]
+  const int32_t* tile_expert;
+  const int32_t* num_m_tiles_ptr;  // device scalar: number of live M tiles
+  int n_per_expert;
 };
 
 template <int BN>
@@ -78,7 +82,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
-  const int num_m = (p.M + kBlockM - 1) / kBlockM;
+  const int num_m = p.num_m_tiles_ptr != nullptr ? min(*p.num_m_tiles_ptr, (p.M + kBlockM - 1) / kBlockM)
+                                                 : (p.M + kBlockM - 1) / kBlockM;
   const int num_n = (p.N + BN - 1) / BN;
   const int num_tiles = num_m * num_n;
   const int num_kb = (p.K + kBlockK - 1) / kBlockK;
@@ -113,6 +118,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int m0 = (tile % num_m) * kBlockM;
         const int n0 = (tile / num_m) * BN;
+        const int b_row_off = p.tile_expert != nullptr ? p.tile_expert[tile % num_m] * p.n_per_expert : 0;
         if (p.a_ready != nullptr) {
           // all-gather ⊕ GEMM: wait until every row block of this M tile has landed.
           const int m1 = min(m0 + kBlockM, p.M);
@@ -140,7 +146,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           uint8_t* sb = sa + Cfg::kABytes;
           mbar_expect_tx(&full_bar[s], Cfg::kStageBytes);
           tma_load_2d(sa, &tmap_a, &full_bar[s], kb * kBlockK, m0, kEvictNormal);
-          tma_load_2d(sb, &tmap_b, &full_bar[s], kb * kBlockK, n0, kEvictNormal);
+          tma_load_2d(sb, &tmap_b, &full_bar[s], kb * kBlockK, n0 + b_row_off, kEvictNormal);
         }
       }
     }
@@ -381,7 +387,7 @@ GLLM_EXPORT int gllm_gemm_bf16(const void* A, int64_t lda, const void* W, int64_
     static int pf = -1;
     if (pf < 0) {
       const char* e = getenv("GLLM_GEMM_PREFETCH");
-      pf = e ? atoi(e) : 24;
+      pf = e ? atoi(e) : 0;  // measured: no gain on B200 (profiles/gemm_bf16_v1.md)
     }
     // prefetching only pays when the weights are streamed once (few M tiles share them)
     p.prefetch_kb = (M <= 1024) ? pf : 0;
@@ -427,4 +433,30 @@ GLLM_EXPORT int gllm_gemm_bf16_tiles_covering(int M, int N, int epi, int force_b
   const int t0 = row0 / kBlockM;
   const int t1 = (row1 - 1) / kBlockM;
   return (t1 - t0 + 1) * ((N + bn - 1) / bn);
+}
+
+// Grouped (MoE) GEMM: rows of A are expert-sorted and padded to 128-row tiles; tile t uses the weight
+// slab W[tile_expert[t]] ([E, N, K] contiguous). The live tile count is read on the device.
+// epi: 0 store, 1 SiLU-gate (slab rows interleaved per 64 like the dense gate/up weight).
+GLLM_EXPORT int gllm_moe_grouped_gemm(const void* A, int64_t lda, const void* W, void* C, int64_t ldc,
+                                      int max_tiles, int N, int K, int E, const void* tile_expert,
+                                      const void* num_tiles_ptr, int epi, void* stream) {
+  if (max_tiles <= 0) return 0;
+  if ((K % 8) != 0 || (N % 8) != 0 || (lda % 8) != 0 || (ldc % 8) != 0) return 1;
+  const int bn = 128;  // 64|64 gate/up interleave for the SiLU epilogue; good balance for expert tiles
+  CUtensorMap ta, tb;
+  const int M = max_tiles * kBlockM;
+  if (make_tmap_2d(&ta, A, M, K, lda * 2, kBlockM, kBlockK, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16)) return 1;
+  if (make_tmap_2d(&tb, W, static_cast<uint64_t>(E) * N, K, static_cast<uint64_t>(K) * 2, bn, kBlockK,
+                   CU_TENSOR_MAP_DATA_TYPE_BFLOAT16)) return 1;
+  GemmParams p;
+  memset(&p, 0, sizeof(p));
+  p.M = M; p.N = N; p.K = K;
+  p.C = reinterpret_cast<__nv_bfloat16*>(C);
+  p.ldc = static_cast<int>(ldc);
+  p.tile_expert = reinterpret_cast<const int32_t*>(tile_expert);
+  p.num_m_tiles_ptr = reinterpret_cast<const int32_t*>(num_tiles_ptr);
+  p.n_per_expert = N;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  return epi == kEpiSiluMul ? launch_gemm<128, kEpiSiluMul>(ta, tb, p, st) : launch_gemm<128, kEpiStore>(ta, tb, p, st);
 }

@@ -132,22 +132,23 @@ gemm_smallm_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_cons
     const int q = warp & 3;
     const int et = q * 32 + lane;  // 0..127 : weight row inside the tile == TMEM lane
     uint32_t tcount = 0;
+    const bool direct = (p.S == 1 && !p.silu);
     for (int u = blockIdx.x; u < num_units; u += gridDim.x, ++tcount) {
-      const int nt = u / p.S, sp = u % p.S;
+      const int nt = u / p.S;
       const uint32_t buf = tcount & 1, aph = (tcount >> 1) & 1;
       mbar_wait(&tmem_full[buf], aph);
       tc_fence_after();
       const uint32_t t_row = tmem_base + buf * p.BT + (static_cast<uint32_t>(q * 32) << 16);
       const int n = nt * kWTile + et;
-      const bool direct = (p.S == 1 && !p.silu);
-      float* wsp = p.ws + (static_cast<size_t>(u) * kWTile + et) * p.BT;
+      // partial tile in the workspace is token-major: ws[unit][m][128] -> every warp store is 128 B
+      float* __restrict__ wsu = p.ws + static_cast<size_t>(u) * p.BT * kWTile + et;
+      const float b = (direct && p.bias != nullptr && n < p.N) ? __bfloat162float(p.bias[n]) : 0.f;
       for (int c = 0; c < p.BT; c += 16) {
         uint32_t v[16];
         tmem_ld_32x16(t_row + c, v);
         tmem_ld_wait();
         if (direct) {
           if (n < p.N) {
-            const float b = p.bias != nullptr ? __bfloat162float(p.bias[n]) : 0.f;
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
               const int m = c + j;
@@ -156,8 +157,8 @@ gemm_smallm_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_cons
           }
         } else {
 #pragma unroll
-          for (int j = 0; j < 16; j += 4) {
-            *reinterpret_cast<uint4*>(wsp + c + j) = make_uint4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+          for (int j = 0; j < 16; ++j) {
+            if (c + j < p.M) wsu[static_cast<size_t>(c + j) * kWTile] = __uint_as_float(v[j]);
           }
         }
       }
@@ -166,7 +167,7 @@ gemm_smallm_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_cons
       if (lane == 0) mbar_arrive(&tmem_empty[buf]);
       if (direct) continue;
 
-      // publish the partial tile; the last split to arrive reduces
+      // publish the partial tile; the last split to arrive reduces (fixed order => deterministic)
       __threadfence();
       asm volatile("bar.sync 1, 128;" ::: "memory");
       if (et == 0) {
@@ -176,43 +177,76 @@ gemm_smallm_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_cons
       asm volatile("bar.sync 1, 128;" ::: "memory");
       if (*flag_smem) {
         __threadfence();
-        const float* base = p.ws + (static_cast<size_t>(nt) * p.S) * kWTile * p.BT;
+        const float* __restrict__ base = p.ws + static_cast<size_t>(nt) * p.S * p.BT * kWTile;
+        const size_t unit_stride = static_cast<size_t>(p.BT) * kWTile;
+        const int n4 = et & 31;   // float4 column group
+        const int mr = et >> 5;   // 0..3
+        constexpr int U = 4;      // rows in flight per thread
         if (!p.silu) {
-          if (n < p.N) {
-            const float b = p.bias != nullptr ? __bfloat162float(p.bias[n]) : 0.f;
-            for (int c = 0; c < p.BT; c += 4) {
-              float4 acc = make_float4(b, b, b, b);
-              for (int s2 = 0; s2 < p.S; ++s2) {
-                const float4 t = __ldcg(reinterpret_cast<const float4*>(
-                    base + (static_cast<size_t>(s2) * kWTile + et) * p.BT + c));
-                acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
-              }
-              const float a[4] = {acc.x, acc.y, acc.z, acc.w};
+          const int ncol = nt * kWTile + n4 * 4;
+          float bb[4] = {0.f, 0.f, 0.f, 0.f};
+          if (p.bias != nullptr) {
 #pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                const int m = c + j;
-                if (m < p.M) p.C[static_cast<size_t>(m) * p.ldc + n] = __float2bfloat16(a[j]);
+            for (int j = 0; j < 4; ++j) if (ncol + j < p.N) bb[j] = __bfloat162float(p.bias[ncol + j]);
+          }
+          for (int m0 = 0; m0 < p.M; m0 += 4 * U) {
+            float4 acc[U];
+#pragma unroll
+            for (int uu = 0; uu < U; ++uu) {
+              const int m = m0 + uu * 4 + mr;
+              acc[uu] = make_float4(bb[0], bb[1], bb[2], bb[3]);
+              if (m < p.M) {
+                for (int s2 = 0; s2 < p.S; ++s2) {
+                  const float4 t = __ldcg(reinterpret_cast<const float4*>(
+                      base + s2 * unit_stride + static_cast<size_t>(m) * kWTile + n4 * 4));
+                  acc[uu].x += t.x; acc[uu].y += t.y; acc[uu].z += t.z; acc[uu].w += t.w;
+                }
+              }
+            }
+#pragma unroll
+            for (int uu = 0; uu < U; ++uu) {
+              const int m = m0 + uu * 4 + mr;
+              if (m < p.M) {
+                __nv_bfloat16* dst = p.C + static_cast<size_t>(m) * p.ldc + ncol;
+                if (ncol + 3 < p.N) {
+                  *reinterpret_cast<uint2*>(dst) = make_uint2(pack_bf16(acc[uu].x, acc[uu].y), pack_bf16(acc[uu].z, acc[uu].w));
+                } else {
+                  const float a[4] = {acc[uu].x, acc[uu].y, acc[uu].z, acc[uu].w};
+                  for (int j = 0; j < 4; ++j) if (ncol + j < p.N) dst[j] = __float2bfloat16(a[j]);
+                }
               }
             }
           }
-        } else if (et < 64) {
-          const int f = nt * 64 + et;  // output feature
-          if (f < p.N / 2) {
-            for (int c = 0; c < p.BT; c += 4) {
-              float4 g = make_float4(0.f, 0.f, 0.f, 0.f), uu = g;
-              for (int s2 = 0; s2 < p.S; ++s2) {
-                const float* r = base + (static_cast<size_t>(s2) * kWTile + et) * p.BT + c;
-                const float4 tg = __ldcg(reinterpret_cast<const float4*>(r));
-                const float4 tu = __ldcg(reinterpret_cast<const float4*>(r + static_cast<size_t>(64) * p.BT));
-                g.x += tg.x; g.y += tg.y; g.z += tg.z; g.w += tg.w;
-                uu.x += tu.x; uu.y += tu.y; uu.z += tu.z; uu.w += tu.w;
-              }
-              const float ga[4] = {g.x, g.y, g.z, g.w}, ua[4] = {uu.x, uu.y, uu.z, uu.w};
+        } else if (n4 < 16) {
+          // gate columns [0,64), up columns [64,128) of the same 64 output features
+          const int f = nt * 64 + n4 * 4;
+          for (int m0 = 0; m0 < p.M; m0 += 4 * U) {
+            float4 g[U], up[U];
 #pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                const int m = c + j;
-                if (m < p.M)
-                  p.C[static_cast<size_t>(m) * p.ldc + f] = __float2bfloat16(ga[j] / (1.f + __expf(-ga[j])) * ua[j]);
+            for (int uu = 0; uu < U; ++uu) {
+              const int m = m0 + uu * 4 + mr;
+              g[uu] = make_float4(0.f, 0.f, 0.f, 0.f);
+              up[uu] = g[uu];
+              if (m < p.M) {
+                for (int s2 = 0; s2 < p.S; ++s2) {
+                  const float* r = base + s2 * unit_stride + static_cast<size_t>(m) * kWTile + n4 * 4;
+                  const float4 tg = __ldcg(reinterpret_cast<const float4*>(r));
+                  const float4 tu = __ldcg(reinterpret_cast<const float4*>(r + 64));
+                  g[uu].x += tg.x; g[uu].y += tg.y; g[uu].z += tg.z; g[uu].w += tg.w;
+                  up[uu].x += tu.x; up[uu].y += tu.y; up[uu].z += tu.z; up[uu].w += tu.w;
+                }
+              }
+            }
+#pragma unroll
+            for (int uu = 0; uu < U; ++uu) {
+              const int m = m0 + uu * 4 + mr;
+              if (m < p.M && f + 3 < p.N / 2) {
+                const float o0 = g[uu].x / (1.f + __expf(-g[uu].x)) * up[uu].x;
+                const float o1 = g[uu].y / (1.f + __expf(-g[uu].y)) * up[uu].y;
+                const float o2 = g[uu].z / (1.f + __expf(-g[uu].z)) * up[uu].z;
+                const float o3 = g[uu].w / (1.f + __expf(-g[uu].w)) * up[uu].w;
+                *reinterpret_cast<uint2*>(p.C + static_cast<size_t>(m) * p.ldc + f) =
+                    make_uint2(pack_bf16(o0, o1), pack_bf16(o2, o3));
               }
             }
           }
@@ -260,10 +294,18 @@ GLLM_EXPORT int gllm_gemm_smallm(const void* A, int64_t lda, const void* W, int6
     const int units = num_n * s;
     if ((s > 1 || silu) && static_cast<int64_t>(units) * kWTile * p.BT > ws_floats) continue;
     const int waves = (units + sms - 1) / sms;
-    const double cost = waves * (kbs + 6.0) + (s > 1 ? 1.5 : 0.0);
+    // unit of cost = one k-block of this shape (fill-bound: (16 KB + BT*128 B) / 64 B/clk)
+    const double kb_cyc = 256.0 + 2.0 * p.BT;
+    const double ovh = 2.0 + 30.0 * p.BT / kb_cyc;                // prologue + TMEM drain/store per unit
+    const double red = (s > 1) ? 4.0 * M * s / kb_cyc : 0.0;      // last-arriver reduction
+    const double cost = waves * (kbs + ovh) + red;
     if (cost < best_cost - 1e-9) { best_cost = cost; best_s = s; }
   }
-  if (force_split > 0) best_s = force_split;
+  if (force_split > 0) {
+    best_s = force_split;
+    while (best_s > 1 && ((best_s - 1) * ((num_kb + best_s - 1) / best_s) >= num_kb ||
+                          static_cast<int64_t>(num_n) * best_s * kWTile * p.BT > ws_floats)) --best_s;
+  }
   p.S = best_s;
   p.kb_per_split = (num_kb + p.S - 1) / p.S;
   if (static_cast<int64_t>(num_n) * p.S * kWTile * p.BT > ws_floats && !(p.S == 1 && !silu)) {

@@ -63,6 +63,11 @@ def _declare(lib):
     sig("gllm_attn_prefill", [P, L, P, P, P, L, P, P, P, I, I, I, I, I, I, I, I, F, P])
     sig("gllm_sample", [P, I, L, P, I, I, P, P, P, P, P, I, P, c_uint64, P, P, I, P])
     sig("gllm_mark_seen", [P, I, P, P, I, P])
+    sig("gllm_moe_topk_softmax", [P, L, P, P, I, I, I, I, P])
+    sig("gllm_moe_grouped_topk", [P, L, P, P, P, I, I, I, I, I, I, I, F, P])
+    sig("gllm_moe_align_gather", [P, P, I, I, I, P, P, I, P, P, L, P, I, P])
+    sig("gllm_moe_grouped_gemm", [P, L, P, P, L, I, I, I, I, P, P, I, P])
+    sig("gllm_moe_combine", [P, P, P, P, I, I, I, P])
 
 
 def load():

@@ -39,7 +39,8 @@ def _count(n=1):
 # GEMM
 # ----------------------------------------------------------------------------------------------
 _FORCE_BN = int(os.environ.get("GLLM_GEMM_BN", "0"))
-_SMALLM_MAX = int(os.environ.get("GLLM_GEMM_SMALLM_MAX", "256"))   # M <= this -> swap-AB split-K kernel
+_SMALLM_MAX = int(os.environ.get("GLLM_GEMM_SMALLM_MAX", "32"))   # M <= this -> swap-AB split-K kernel
+# (measured crossover vs the 128xBN kernel on B200: profiles/gemm_smallm.md)
 _FORCE_SPLIT = int(os.environ.get("GLLM_GEMM_SPLIT", "0"))
 _SMALLM_WS_FLOATS = 24 << 20
 _smallm_ws = {}

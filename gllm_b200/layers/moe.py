@@ -80,11 +80,16 @@ class FusedMoE(nn.Module):
             return
         le = global_e - self.e_start
         if self.use_ep or self.tp_size == 1:
-            self.w13.data[le].copy_(torch.cat([gate, up], dim=0))
-            self.w2.data[le].copy_(down)
+            gu = torch.cat([gate, up], dim=0)
         else:
-            self.w13.data[le].copy_(wu.shard_gate_up(gate, up, self.tp_rank, self.tp_size))
-            self.w2.data[le].copy_(wu.shard_cols(down, self.tp_rank, self.tp_size))
+            gu = wu.shard_gate_up(gate, up, self.tp_rank, self.tp_size)
+            down = wu.shard_cols(down, self.tp_rank, self.tp_size)
+        if self.w13.is_cuda:
+            # the grouped GEMM's SiLU-gate epilogue wants gate/up rows interleaved per 64
+            assert self.inter % 64 == 0, "sm_100a MoE path needs intermediate % 64 == 0"
+            gu = ref.interleave_gate_up(gu, 64)
+        self.w13.data[le].copy_(gu)
+        self.w2.data[le].copy_(down)
 
 
 def _sm_grouped_topk(moe: FusedMoE, logits):
@@ -128,16 +133,24 @@ class SparseMoeBlock(nn.Module):
         ex.router_w.data.copy_(reader.get(pre + nm["router"]))
         if ex.e_bias is not None and "router_bias" in nm and reader.has(pre + nm["router_bias"]):
             ex.e_bias.data.copy_(reader.get(pre + nm["router_bias"]).float())
-        fused_name = nm.get("experts_fused_gate_up")
-        if fused_name and reader.has(pre + fused_name):
-            # Qwen3-VL-MoE: experts.gate_up_proj [E, H, 2I], experts.down_proj [E, I, H]
+        fused_name = nm.get("experts_fused_gate_up", "mlp.experts.gate_up_proj")
+        first_expert = pre + nm["expert"].format(e=ex.e_start) + nm["e_gate"]
+        if not reader.has(first_expert) and reader.has(pre + fused_name):
+            # fused expert tensors: Qwen3-VL-MoE stores [E, H, 2I] / [E, I, H] (transposed);
+            # transformers>=5 in-memory layout is [E, 2I, H] / [E, H, I]
             gu = reader.get(pre + fused_name)
-            dn = reader.get(pre + nm["experts_fused_down"])
-            inter = gu.shape[-1] // 2
+            dn = reader.get(pre + nm.get("experts_fused_down", "mlp.experts.down_proj"))
+            transposed = gu.shape[1] == ex.hidden and gu.shape[2] != ex.hidden
             for e in range(ex.e_start, ex.e_start + ex.e_local):
-                g = gu[e, :, :inter].t().contiguous()
-                u = gu[e, :, inter:].t().contiguous()
-                ex.load_expert(e, g, u, dn[e].t().contiguous())
+                if transposed:
+                    inter = gu.shape[-1] // 2
+                    g = gu[e, :, :inter].t().contiguous()
+                    u = gu[e, :, inter:].t().contiguous()
+                    d = dn[e].t().contiguous()
+                else:
+                    inter = gu.shape[1] // 2
+                    g, u, d = gu[e, :inter], gu[e, inter:], dn[e]
+                ex.load_expert(e, g, u, d)
         else:
             for e in range(ex.e_start, ex.e_start + ex.e_local):
                 ep = pre + nm["expert"].format(e=e)

@@ -83,7 +83,8 @@ def _moe_layers(cfg, n_layers):
 def spec_qwen2_moe(cfg):
     spec = spec_qwen2(cfg)
     spec.arch = "qwen2_moe"
-    spec.moe = MoESpec(num_experts=cfg["num_experts"], top_k=cfg["num_experts_per_tok"],
+    spec.moe = MoESpec(num_experts=cfg.get("num_experts") or cfg["num_local_experts"],
+                       top_k=cfg["num_experts_per_tok"],
                        intermediate_size=cfg["moe_intermediate_size"],
                        norm_topk_prob=bool(cfg.get("norm_topk_prob", False)),
                        shared_intermediate_size=cfg.get("shared_expert_intermediate_size", 0) or 0,
@@ -95,7 +96,8 @@ def spec_qwen2_moe(cfg):
 def spec_qwen3_moe(cfg):
     spec = spec_qwen3(cfg)
     spec.arch = "qwen3_moe"
-    spec.moe = MoESpec(num_experts=cfg["num_experts"], top_k=cfg["num_experts_per_tok"],
+    spec.moe = MoESpec(num_experts=cfg.get("num_experts") or cfg["num_local_experts"],
+                       top_k=cfg["num_experts_per_tok"],
                        intermediate_size=cfg["moe_intermediate_size"],
                        norm_topk_prob=bool(cfg.get("norm_topk_prob", True)))
     spec.moe_layers = _moe_layers(cfg, spec.num_layers)

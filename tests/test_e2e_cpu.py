@@ -131,3 +131,33 @@ def test_eos_and_output_len_finish():
     with pytest.raises(ValueError):
         llm.generate(tokens=[[1] * 400], output_lens=[4])
     llm.shutdown()
+
+
+def test_mixtral_matches_hf():
+    from transformers import MixtralConfig, MixtralForCausalLM
+    torch.manual_seed(6)
+    cfg = MixtralConfig(hidden_size=64, intermediate_size=128, num_hidden_layers=2, num_attention_heads=4,
+                        num_key_value_heads=2, vocab_size=512, max_position_embeddings=512, num_local_experts=4,
+                        num_experts_per_tok=2, eos_token_id=1, sliding_window=None)
+    _check(MixtralForCausalLM(cfg).eval().float())
+
+
+def test_qwen3_moe_matches_hf():
+    from transformers import Qwen3MoeConfig, Qwen3MoeForCausalLM
+    torch.manual_seed(7)
+    cfg = Qwen3MoeConfig(hidden_size=64, intermediate_size=128, moe_intermediate_size=64, num_hidden_layers=2,
+                         num_attention_heads=4, num_key_value_heads=2, head_dim=16, vocab_size=512,
+                         max_position_embeddings=512, num_experts=8, num_experts_per_tok=2, norm_topk_prob=True,
+                         decoder_sparse_step=1, mlp_only_layers=[], eos_token_id=1)
+    _check(Qwen3MoeForCausalLM(cfg).eval().float())
+
+
+def test_qwen2_moe_shared_expert_matches_hf():
+    from transformers import Qwen2MoeConfig, Qwen2MoeForCausalLM
+    torch.manual_seed(8)
+    cfg = Qwen2MoeConfig(hidden_size=64, intermediate_size=128, moe_intermediate_size=64,
+                         shared_expert_intermediate_size=128, num_hidden_layers=2, num_attention_heads=4,
+                         num_key_value_heads=2, vocab_size=512, max_position_embeddings=512, num_experts=4,
+                         num_experts_per_tok=2, norm_topk_prob=False, decoder_sparse_step=1, mlp_only_layers=[],
+                         eos_token_id=1)
+    _check(Qwen2MoeForCausalLM(cfg).eval().float())

@@ -269,6 +269,7 @@ def test_gemm_smallm(m, n, k, split, monkeypatch):
     """swap-AB split-K decode GEMM (bias, forced splits, ragged N)."""
     from gllm_b200.ops import sm100
     monkeypatch.setattr(sm100, "_FORCE_SPLIT", split)
+    monkeypatch.setattr(sm100, "_SMALLM_MAX", 256)
     torch.manual_seed(m + n)
     x = (torch.randn(m, k, device=_dev()) * 0.5).bfloat16()
     w = (torch.randn(n, k, device=_dev()) * 0.05).bfloat16()
@@ -287,6 +288,7 @@ def test_gemm_smallm(m, n, k, split, monkeypatch):
 def test_gemm_smallm_silu(m, split, monkeypatch):
     from gllm_b200.ops import sm100
     monkeypatch.setattr(sm100, "_FORCE_SPLIT", split)
+    monkeypatch.setattr(sm100, "_SMALLM_MAX", 256)
     torch.manual_seed(m)
     i, k = 1536, 1024
     x = (torch.randn(m, k, device=_dev()) * 0.5).bfloat16()
@@ -295,3 +297,52 @@ def test_gemm_smallm_silu(m, split, monkeypatch):
     h = x.float() @ w.float().t()
     yr = torch.nn.functional.silu(h[:, :i]) * h[:, i:]
     assert _rel_err(y, yr) < 1e-2
+
+
+@pytest.mark.parametrize("e,k,renorm", [(8, 2, True), (60, 4, False), (128, 8, True), (256, 8, True)])
+def test_moe_topk_softmax(e, k, renorm):
+    from gllm_b200.ops import sm100_moe
+    torch.manual_seed(e)
+    logits = torch.randn(77, e, device=_dev()).bfloat16()
+    w, ids = sm100_moe.topk_softmax(logits, k, renorm)
+    w_r, ids_r = ref.topk_softmax(logits, k, renorm)
+    # compare as sets per row (tie order may differ), weights by id
+    dense = torch.zeros(77, e, device=_dev()).scatter(1, ids.long(), w)
+    dense_r = torch.zeros(77, e, device=_dev()).scatter(1, ids_r.long(), w_r)
+    assert torch.allclose(dense, dense_r, atol=2e-3, rtol=1e-2)
+
+
+@pytest.mark.parametrize("scoring,bias", [("sigmoid", True), ("softmax", False)])
+def test_moe_grouped_topk(scoring, bias):
+    from gllm_b200.ops import sm100_moe
+    torch.manual_seed(11)
+    t, e, k, g, tg = 93, 256, 8, 8, 4
+    logits = torch.randn(t, e, device=_dev()).bfloat16()
+    b = (torch.randn(e, device=_dev()) * 0.1).float() if bias else None
+    w, ids = sm100_moe.grouped_topk(logits, k, True, g, tg, scoring, b, 2.5)
+    w_r, ids_r = ref.grouped_topk(logits, k, True, g, tg, scoring, b, 2.5)
+    dense = torch.zeros(t, e, device=_dev()).scatter(1, ids.long(), w)
+    dense_r = torch.zeros(t, e, device=_dev()).scatter(1, ids_r.long(), w_r)
+    assert torch.allclose(dense, dense_r, atol=5e-3, rtol=2e-2)
+
+
+@pytest.mark.parametrize("t,e,k,h,i,ep", [(5, 8, 2, 256, 512, False), (300, 8, 2, 512, 1024, False),
+                                          (200, 16, 4, 256, 256, True), (1000, 64, 6, 256, 128, False)])
+def test_moe_fused_experts(t, e, k, h, i, ep):
+    from gllm_b200.ops import sm100_moe
+    torch.manual_seed(t + e)
+    x = (torch.randn(t, h, device=_dev()) * 0.5).bfloat16()
+    e_local = e // 2 if ep else e
+    w13 = (torch.randn(e_local, 2 * i, h, device=_dev()) * 0.05).bfloat16()
+    w2 = (torch.randn(e_local, h, i, device=_dev()) * 0.05).bfloat16()
+    logits = torch.randn(t, e, device=_dev()).bfloat16()
+    w, ids = ref.topk_softmax(logits, k, True)
+    emap = None
+    if ep:
+        emap = torch.full((e,), -1, dtype=torch.int32, device=_dev())
+        emap[e // 2:] = torch.arange(e_local, dtype=torch.int32, device=_dev())
+    w13_il = torch.stack([ref.interleave_gate_up(w13[j], 64) for j in range(e_local)])
+    y = sm100_moe.fused_experts(x, w13_il, w2, w, ids, emap)
+    y_ref = ref.fused_experts(x, w13, w2, w, ids, emap)
+    assert torch.isfinite(y.float()).all()
+    assert _rel_err(y, y_ref) < 2e-2, _rel_err(y, y_ref)

@@ -1,0 +1,273 @@
+// Tensor-parallel collectives fused into the compute kernels, over NVLink peer memory (P2P ld/st
+// on symmetric buffers). Together with the hooks in gemm/gemm_bf16.cu these implement the
+// token-sharded ("sequence parallel") block dataflow that replaces the reference's
+// GEMM -> NCCL all_reduce -> fused_add_rms_norm (gllm/layers/linear.py:247-250):
+//
+//   row-parallel GEMM  ⊕ reduce-scatter : the GEMM epilogue stores every partial tile straight into
+//        the owner rank's staging slot   stage[owner][src][row_local][H]   and bumps
+//        cnt[owner][src] with red.release.sys   (gemm_bf16.cu, rs_* params)
+//   rs_reduce_norm (this file)          : owner waits for the tile counters, sums the tp partials in a
+//        fixed order (deterministic), adds the residual shard, applies RMSNorm and PUSHES the normed
+//        rows into every peer's gather buffer (all-gather by producer-side stores), then publishes an
+//        epoch flag per peer with st.release.sys
+//   column-parallel GEMM ⊕ all-gather   : the next GEMM's TMA producer warp spins (ld.acquire.sys) on
+//        the flags of the row shards that cover its M tile before loading A   (gemm_bf16.cu, a_ready)
+//
+// Everything is CUDA-graph safe: no host-side epochs — expected counter values and flag epochs live
+// in device memory and are advanced by the kernels themselves.
+#include "../common/host_utils.h"
+#include "../common/ptx.cuh"
+
+namespace b200 {
+
+static constexpr int kMaxTp = 8;
+
+struct TpState {
+  // device-resident, one per rank (NOT symmetric): advanced by the kernels
+  uint32_t rs_expected[2][kMaxTp];  // per parity, per source rank: tile arrivals consumed so far
+  uint32_t ag_epoch[3];             // per gather buffer: epoch published by the last push
+  uint32_t ticket[4];               // grid tickets
+};
+
+struct ReduceNormParams {
+  // partial sources: stage slots of this rank (local memory), [src][rows_per_rank][H]
+  const __nv_bfloat16* stage;
+  const uint32_t* cnt;          // [kMaxTp] arrival counters for this parity (local, written by peers)
+  uint32_t n_tiles[kMaxTp];     // arrivals expected from each source this call
+  const __nv_bfloat16* local_x; // != null: single local source (rows of this rank's shard), no waiting
+  int64_t local_ld;
+  __nv_bfloat16* residual;      // [rows_per_rank, H] shard (in/out); may be null on first use
+  int residual_in;              // 0: residual := sum (first layer), 1: residual += sum
+  const __nv_bfloat16* norm_w;
+  __nv_bfloat16* ag_peers[kMaxTp];  // gather buffer [T_pad, H] of every rank (peer pointers)
+  uint32_t* flag_peers[kMaxTp];     // flags[tp] of every rank for this gather buffer
+  __nv_bfloat16* unnormed_out;      // optional: also store the un-normalised sum (PP boundary)
+  TpState* st;
+  int parity, ag_idx;
+  int tp, rank, rows_per_rank, rows_valid, H;
+  float eps;
+};
+
+template <int NV>
+__global__ void rs_reduce_norm_kernel(const ReduceNormParams p) {
+  __shared__ float red[32];
+  __shared__ uint32_t s_last;
+  const int row = blockIdx.x;  // local row in this rank's shard
+  const int nvec = p.H >> 3;
+
+  if (p.local_x == nullptr && threadIdx.x < p.tp) {
+    const int src = threadIdx.x;
+    const uint32_t target = p.st->rs_expected[p.parity][src] + p.n_tiles[src];
+    const uint32_t* c = p.cnt + src;
+    // wrap-safe comparison on monotonically increasing counters
+    while (static_cast<int32_t>(ld_acquire_sys(c) - target) < 0) {
+    }
+  }
+  __syncthreads();
+
+  float v[NV][8];
+  float ss = 0.f;
+  if (row < p.rows_valid) {
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+      const int i = threadIdx.x + j * blockDim.x;
+      if (i < nvec) {
+        float a[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        if (p.local_x != nullptr) {
+          const uint4 t = *reinterpret_cast<const uint4*>(
+              p.local_x + (static_cast<size_t>(p.rank) * p.rows_per_rank + row) * p.local_ld + i * 8);
+          const float2 f0 = unpack_bf16(t.x), f1 = unpack_bf16(t.y), f2 = unpack_bf16(t.z), f3 = unpack_bf16(t.w);
+          a[0] = f0.x; a[1] = f0.y; a[2] = f1.x; a[3] = f1.y; a[4] = f2.x; a[5] = f2.y; a[6] = f3.x; a[7] = f3.y;
+        } else {
+          for (int s = 0; s < p.tp; ++s) {
+            const uint4 t = __ldcg(reinterpret_cast<const uint4*>(
+                p.stage + (static_cast<size_t>(s) * p.rows_per_rank + row) * p.H + i * 8));
+            const float2 f0 = unpack_bf16(t.x), f1 = unpack_bf16(t.y), f2 = unpack_bf16(t.z), f3 = unpack_bf16(t.w);
+            a[0] += f0.x; a[1] += f0.y; a[2] += f1.x; a[3] += f1.y; a[4] += f2.x; a[5] += f2.y; a[6] += f3.x; a[7] += f3.y;
+          }
+        }
+        if (p.unnormed_out != nullptr) {
+          uint4 o;
+          o.x = pack_bf16(a[0], a[1]); o.y = pack_bf16(a[2], a[3]); o.z = pack_bf16(a[4], a[5]); o.w = pack_bf16(a[6], a[7]);
+          *reinterpret_cast<uint4*>(p.unnormed_out + static_cast<size_t>(row) * p.H + i * 8) = o;
+        }
+        if (p.residual != nullptr) {
+          __nv_bfloat16* rp = p.residual + static_cast<size_t>(row) * p.H + i * 8;
+          if (p.residual_in) {
+            const uint4 r = *reinterpret_cast<const uint4*>(rp);
+            const float2 r0 = unpack_bf16(r.x), r1 = unpack_bf16(r.y), r2 = unpack_bf16(r.z), r3 = unpack_bf16(r.w);
+            // the all-reduced value is rounded to bf16 before the add, like the unfused reference
+            a[0] = __bfloat162float(__float2bfloat16(a[0])) + r0.x; a[1] = __bfloat162float(__float2bfloat16(a[1])) + r0.y;
+            a[2] = __bfloat162float(__float2bfloat16(a[2])) + r1.x; a[3] = __bfloat162float(__float2bfloat16(a[3])) + r1.y;
+            a[4] = __bfloat162float(__float2bfloat16(a[4])) + r2.x; a[5] = __bfloat162float(__float2bfloat16(a[5])) + r2.y;
+            a[6] = __bfloat162float(__float2bfloat16(a[6])) + r3.x; a[7] = __bfloat162float(__float2bfloat16(a[7])) + r3.y;
+          }
+          uint4 o;
+          o.x = pack_bf16(a[0], a[1]); o.y = pack_bf16(a[2], a[3]); o.z = pack_bf16(a[4], a[5]); o.w = pack_bf16(a[6], a[7]);
+          *reinterpret_cast<uint4*>(rp) = o;
+          const float2 q0 = unpack_bf16(o.x), q1 = unpack_bf16(o.y), q2 = unpack_bf16(o.z), q3 = unpack_bf16(o.w);
+          a[0] = q0.x; a[1] = q0.y; a[2] = q1.x; a[3] = q1.y; a[4] = q2.x; a[5] = q2.y; a[6] = q3.x; a[7] = q3.y;
+        }
+#pragma unroll
+        for (int e = 0; e < 8; ++e) { v[j][e] = a[e]; ss += a[e] * a[e]; }
+      }
+    }
+  }
+  // block reduce
+  {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    if (lane == 0) red[warp] = ss;
+    __syncthreads();
+    float t = lane < ((blockDim.x + 31) >> 5) ? red[lane] : 0.f;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    ss = t;
+  }
+  if (row < p.rows_valid && p.norm_w != nullptr) {
+    const float inv = rsqrtf(ss / static_cast<float>(p.H) + p.eps);
+    const size_t grow = static_cast<size_t>(p.rank) * p.rows_per_rank + row;
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+      const int i = threadIdx.x + j * blockDim.x;
+      if (i < nvec) {
+        const uint4 wv = *reinterpret_cast<const uint4*>(p.norm_w + i * 8);
+        const float2 w0 = unpack_bf16(wv.x), w1 = unpack_bf16(wv.y), w2 = unpack_bf16(wv.z), w3 = unpack_bf16(wv.w);
+        uint4 o;
+        o.x = pack_bf16(v[j][0] * inv * w0.x, v[j][1] * inv * w0.y);
+        o.y = pack_bf16(v[j][2] * inv * w1.x, v[j][3] * inv * w1.y);
+        o.z = pack_bf16(v[j][4] * inv * w2.x, v[j][5] * inv * w2.y);
+        o.w = pack_bf16(v[j][6] * inv * w3.x, v[j][7] * inv * w3.y);
+        // all-gather by producer-side stores: own copy first, then the peers (rank-rotated order)
+        for (int d = 0; d < p.tp; ++d) {
+          const int peer = (p.rank + d) % p.tp;
+          st_v4(p.ag_peers[peer] + grow * p.H + i * 8, o);
+        }
+      }
+    }
+  }
+  // publish: the last CTA of the grid bumps the bookkeeping and raises the flags on every peer
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const uint32_t old = atomicAdd(&p.st->ticket[0], 1u);
+    s_last = (old == gridDim.x - 1) ? 1u : 0u;
+  }
+  __syncthreads();
+  if (s_last) {
+    if (threadIdx.x == 0) {
+      p.st->ticket[0] = 0u;
+      if (p.local_x == nullptr)
+        for (int s = 0; s < p.tp; ++s) p.st->rs_expected[p.parity][s] += p.n_tiles[s];
+      const uint32_t e = p.st->ag_epoch[p.ag_idx] + 1u;
+      p.st->ag_epoch[p.ag_idx] = e;
+      __threadfence_system();
+      for (int d = 0; d < p.tp; ++d) {
+        const int peer = (p.rank + d) % p.tp;
+        st_release_sys(p.flag_peers[peer] + p.rank, e);
+      }
+    }
+  }
+}
+
+// Push a full-length partial [T, H] (e.g. the MoE block output, or anything not produced by the fused
+// GEMM epilogue) into the owners' staging slots; one CTA per row, one arrival per row.
+__global__ void push_partial_rows_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, int T, int H, int rank,
+                                         int rows_per_rank, __nv_bfloat16* const* stage_peers,
+                                         uint32_t* const* cnt_peers) {
+  const int row = blockIdx.x;
+  if (row >= T) return;
+  const int owner = row / rows_per_rank;
+  const int rl = row - owner * rows_per_rank;
+  __nv_bfloat16* dst = stage_peers[owner] + (static_cast<size_t>(rank) * rows_per_rank + rl) * H;
+  const __nv_bfloat16* src = x + static_cast<size_t>(row) * ldx;
+  for (int i = threadIdx.x * 8; i < H; i += blockDim.x * 8) st_v4(dst + i, *reinterpret_cast<const uint4*>(src + i));
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) red_add_release_sys(cnt_peers[owner] + rank, 1u);
+}
+
+// Block the stream until the shards of a gather buffer have been published for the current epoch
+// (for consumers that are not the flag-aware GEMM: row gathers, router, ...).
+__global__ void wait_ag_flags_kernel(const uint32_t* flags, const TpState* st, int ag_idx, int tp) {
+  if (threadIdx.x < tp) {
+    const uint32_t e = st->ag_epoch[ag_idx];
+    while (static_cast<int32_t>(ld_acquire_sys(flags + threadIdx.x) - e) < 0) {
+    }
+  }
+}
+
+}  // namespace b200
+
+using namespace b200;
+
+struct ReduceNormArgs {
+  const void* stage;
+  const void* cnt;
+  uint32_t n_tiles[kMaxTp];
+  const void* local_x;
+  int64_t local_ld;
+  void* residual;
+  int residual_in;
+  const void* norm_w;
+  void* ag_peers[kMaxTp];
+  void* flag_peers[kMaxTp];
+  void* unnormed_out;
+  void* st;
+  int parity, ag_idx, tp, rank, rows_per_rank, rows_valid, H;
+  float eps;
+};
+
+GLLM_EXPORT int gllm_rs_reduce_norm(const ReduceNormArgs* a, void* stream) {
+  ReduceNormParams p;
+  p.stage = reinterpret_cast<const __nv_bfloat16*>(a->stage);
+  p.cnt = reinterpret_cast<const uint32_t*>(a->cnt);
+  for (int i = 0; i < kMaxTp; ++i) {
+    p.n_tiles[i] = a->n_tiles[i];
+    p.ag_peers[i] = reinterpret_cast<__nv_bfloat16*>(a->ag_peers[i]);
+    p.flag_peers[i] = reinterpret_cast<uint32_t*>(a->flag_peers[i]);
+  }
+  p.local_x = reinterpret_cast<const __nv_bfloat16*>(a->local_x);
+  p.local_ld = a->local_ld;
+  p.residual = reinterpret_cast<__nv_bfloat16*>(a->residual);
+  p.residual_in = a->residual_in;
+  p.norm_w = reinterpret_cast<const __nv_bfloat16*>(a->norm_w);
+  p.unnormed_out = reinterpret_cast<__nv_bfloat16*>(a->unnormed_out);
+  p.st = reinterpret_cast<TpState*>(a->st);
+  p.parity = a->parity; p.ag_idx = a->ag_idx; p.tp = a->tp; p.rank = a->rank;
+  p.rows_per_rank = a->rows_per_rank; p.rows_valid = a->rows_valid; p.H = a->H; p.eps = a->eps;
+  if (p.H % 8 != 0 || p.tp > kMaxTp) return 1;
+  const int nvec = p.H / 8;
+  int threads = ((nvec + 31) / 32) * 32, nv = 1;
+  while (threads > 1024) { nv *= 2; threads = (((nvec + nv - 1) / nv + 31) / 32) * 32; }
+  if (threads < 32) threads = 32;
+  // one CTA per shard row; at least one CTA so the bookkeeping/flags advance even for empty shards
+  const int grid = p.rows_per_rank > 0 ? p.rows_per_rank : 1;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (nv == 1) rs_reduce_norm_kernel<1><<<grid, threads, 0, st>>>(p);
+  else if (nv == 2) rs_reduce_norm_kernel<2><<<grid, threads, 0, st>>>(p);
+  else if (nv == 4) rs_reduce_norm_kernel<4><<<grid, threads, 0, st>>>(p);
+  else return 1;
+  CUDA_CHECK_RET(cudaGetLastError());
+  return 0;
+}
+
+GLLM_EXPORT int gllm_push_partial_rows(const void* x, int64_t ldx, int T, int H, int rank, int rows_per_rank,
+                                       const void* stage_peers_dev, const void* cnt_peers_dev, void* stream) {
+  if (T <= 0) return 0;
+  push_partial_rows_kernel<<<T, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const __nv_bfloat16*>(x), ldx, T, H, rank, rows_per_rank,
+      reinterpret_cast<__nv_bfloat16* const*>(stage_peers_dev), reinterpret_cast<uint32_t* const*>(cnt_peers_dev));
+  CUDA_CHECK_RET(cudaGetLastError());
+  return 0;
+}
+
+GLLM_EXPORT int gllm_wait_ag_flags(const void* flags, const void* st, int ag_idx, int tp, void* stream) {
+  wait_ag_flags_kernel<<<1, 32, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const uint32_t*>(flags), reinterpret_cast<const TpState*>(st), ag_idx, tp);
+  CUDA_CHECK_RET(cudaGetLastError());
+  return 0;
+}
+
+GLLM_EXPORT int gllm_tp_state_bytes() { return static_cast<int>(sizeof(TpState)); }

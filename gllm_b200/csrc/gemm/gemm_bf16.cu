@@ -37,7 +37,7 @@ struct GemmParams {
   const __nv_bfloat16* bias;
   // all-gather gating (null => disabled)
   const uint32_t* a_ready;
-  uint32_t a_epoch;
+  const uint32_t* a_epoch_ptr;  // device-resident epoch (CUDA-graph safe), see comm/tp_fused.cu
   int rows_per_flag;
   // reduce-scatter push (rs_world == 0 => disabled)
   int rs_world, rs_rank, rows_per_rank;
@@ -124,8 +124,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           const int m1 = min(m0 + kBlockM, p.M);
           const int f0 = m0 / p.rows_per_flag;
           const int f1 = (m1 - 1) / p.rows_per_flag;
+          const uint32_t a_epoch = *reinterpret_cast<const volatile uint32_t*>(p.a_epoch_ptr);
           for (int f = f0; f <= f1; ++f) {
-            while (ld_acquire_sys(p.a_ready + f) < p.a_epoch) {
+            while (static_cast<int32_t>(ld_acquire_sys(p.a_ready + f) - a_epoch) < 0) {
             }
           }
           asm volatile("fence.proxy.async;" ::: "memory");
@@ -357,7 +358,7 @@ using namespace b200;
 // comm: optional pointer to a host-side GemmComm block (may be null).
 struct GemmComm {
   const uint32_t* a_ready;
-  uint32_t a_epoch;
+  const uint32_t* a_epoch_ptr;
   int rows_per_flag;
   int rs_world, rs_rank, rows_per_rank;
   uint32_t rs_inc;
@@ -394,7 +395,7 @@ GLLM_EXPORT int gllm_gemm_bf16(const void* A, int64_t lda, const void* W, int64_
   }
   if (comm != nullptr) {
     p.a_ready = comm->a_ready;
-    p.a_epoch = comm->a_epoch;
+    p.a_epoch_ptr = comm->a_epoch_ptr;
     p.rows_per_flag = comm->rows_per_flag;
     p.rs_world = comm->rs_world;
     p.rs_rank = comm->rs_rank;

@@ -192,7 +192,7 @@ class DecoderLayer(nn.Module):
         a = self.attn(inp, h, kv_cache, tpc)
         h, residual = tpc.row_linear_add_norm(a, self.attn.o_w, residual, self.post_norm_w, eps, self.attn.o_b)
         if self.is_moe:
-            partial = self.mlp(h, tpc)
+            partial = self.mlp(tpc.materialize(h), tpc)
             if next_norm_w is None:
                 return tpc.all_reduce(partial), residual
             return tpc.reduce_add_norm(partial, residual, next_norm_w, eps)
@@ -262,8 +262,7 @@ class CausalLM(nn.Module):
             x = inputs_embeds if inputs_embeds is not None else self.embed(inp, tpc)
             if n == 0:
                 return x, None
-            h, _ = Fn.rmsnorm(x, self.layers[0].input_norm_w, eps)
-            residual = x
+            h, residual = tpc.first_norm(x, self.layers[0].input_norm_w, eps)
         else:
             if n == 0:
                 return hidden, residual
@@ -278,6 +277,7 @@ class CausalLM(nn.Module):
 
     def compute_logits(self, inp, hidden: torch.Tensor, tpc: TPComm, all_rows: bool = False) -> torch.Tensor:
         """Logits of the last token of every emitting sequence -> [E, V]."""
+        hidden = tpc.materialize(hidden)
         rows = hidden if all_rows else Fn.gather_rows(hidden, inp.logits_idx)
         local = Fn.linear(rows, self.lm_head_w)
         return tpc.gather_logits(local, self.spec.vocab_size)

@@ -30,7 +30,7 @@ class GemmComm(ctypes.Structure):
 
     _fields_ = [
         ("a_ready", c_void_p),
-        ("a_epoch", c_uint32),
+        ("a_epoch_ptr", c_void_p),
         ("rows_per_flag", c_int),
         ("rs_world", c_int),
         ("rs_rank", c_int),

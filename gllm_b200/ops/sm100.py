@@ -92,7 +92,8 @@ def linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None
     return out
 
 
-def linear_silu_mul(x: torch.Tensor, w_interleaved: torch.Tensor, out: Optional[torch.Tensor] = None):
+def linear_silu_mul(x: torch.Tensor, w_interleaved: torch.Tensor, out: Optional[torch.Tensor] = None,
+                    comm: Optional[GemmComm] = None):
     """Fused gate/up projection + SiLU-gate epilogue; weight rows interleaved per 64
     (see ops.ref.interleave_gate_up)."""
     # kernels with BN=128 interleave at 64 rows: force BN=128 so tile == [64 gate | 64 up]
@@ -103,11 +104,12 @@ def linear_silu_mul(x: torch.Tensor, w_interleaved: torch.Tensor, out: Optional[
         out = torch.empty(m, n // 2, dtype=_BF16, device=x.device)
     if m == 0:
         return out
-    if m <= _SMALLM_MAX and _FORCE_BN == 0:
+    if m <= _SMALLM_MAX and _FORCE_BN == 0 and comm is None:
         return _linear_smallm(x, w_interleaved, None, out, True)
     L = _lib.load()
     rc = L.gllm_gemm_bf16(_p(x), x.stride(0), _p(w_interleaved), w_interleaved.stride(0), _p(out),
-                          out.stride(0), m, n, k, None, 1, 128, None, stream_ptr())
+                          out.stride(0), m, n, k, None, 1, 128,
+                          ctypes.byref(comm) if comm is not None else None, stream_ptr())
     check(rc, "gemm_bf16(silu)")
     _count()
     return out

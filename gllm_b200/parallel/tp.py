@@ -35,6 +35,15 @@ class TPComm:
     def begin_forward(self, num_tokens: int):
         pass
 
+    def first_norm(self, x: torch.Tensor, norm_w: torch.Tensor, eps: float):
+        """Embedding output -> (normed block input, residual stream)."""
+        h, _ = Fn.rmsnorm(x, norm_w, eps)
+        return h, x
+
+    def materialize(self, h: torch.Tensor) -> torch.Tensor:
+        """Make `h` safe to read by kernels that are not collective-aware (no-op here)."""
+        return h
+
     def col_linear(self, x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None) -> torch.Tensor:
         return Fn.linear(x, w, bias)
 
@@ -73,7 +82,7 @@ class TPComm:
 
 def make_tp_comm(fused: bool = False, **kw) -> TPComm:
     st = ps.get_state()
-    if fused and st.tp_size > 1 and torch.cuda.is_available():
+    if fused and st.tp_size > 1 and st.pp_size == 1 and torch.cuda.is_available():
         from gllm_b200.parallel.fused import FusedTPComm
         return FusedTPComm(**kw)
     return TPComm()

@@ -1,0 +1,111 @@
+"""Multi-GPU check of the fused TP path (run under torchrun, one rank per GPU):
+   1. op level : GEMM⊕reduce-scatter -> add+RMSNorm -> all-gather⊕GEMM  vs  NCCL all_reduce + torch math
+   2. engine   : tokens of tp_mode=fused == tokens of tp_mode=nccl on a small random model
+Prints 'TP_CHECK_OK' on rank 0 on success."""
+import os
+import sys
+
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+
+def main():
+    rank, local, world = int(os.environ["RANK"]), int(os.environ["LOCAL_RANK"]), int(os.environ["WORLD_SIZE"])
+    torch.cuda.set_device(local)
+    from gllm_b200.parallel import state as ps
+    ps.init_dist(1, world, rank, local, os.environ.get("MASTER_ADDR", "127.0.0.1"),
+                 int(os.environ.get("MASTER_PORT", "29500")) + 1)
+    from gllm_b200.ops import ref, sm100
+    from gllm_b200.parallel.fused import FusedTPComm
+    from gllm_b200.parallel.tp import TPComm
+    dev = torch.device("cuda", local)
+    H, K, N2 = 1024, 512, 768
+    fused = FusedTPComm(max_tokens=1024, hidden_size=H, device=dev)
+    base = TPComm()
+    ok = True
+    for T in (1000, 37, 256, 5):
+        torch.manual_seed(100 + T)  # same on every rank
+        x_full = (torch.randn(T, H, device=dev) * 0.5).bfloat16()         # replicated "embedding" output
+        nw0 = (1 + 0.1 * torch.randn(H, device=dev)).bfloat16()
+        nw1 = (1 + 0.1 * torch.randn(H, device=dev)).bfloat16()
+        w_col = (torch.randn(world, N2, H, device=dev) * 0.05).bfloat16()[rank]     # column-parallel shard
+        w_row = (torch.randn(world, H, N2, device=dev) * 0.05).bfloat16()[rank]     # row-parallel shard
+        w_col2 = (torch.randn(world, N2, H, device=dev) * 0.05).bfloat16()[rank]
+        # ---- baseline (NCCL) ----
+        h, res = base.first_norm(x_full.clone(), nw0, 1e-6)
+        res = res.clone()
+        a = base.col_linear(h, w_col)
+        h2, res = base.row_linear_add_norm(a, w_row, res, nw1, 1e-6)
+        y_ref = base.col_linear(h2, w_col2)
+        # ---- fused ----
+        for rep in range(3):  # repeated: exercises parity / epoch bookkeeping
+            fused.begin_forward(T)
+            hf, resf = fused.first_norm(x_full.clone(), nw0, 1e-6)
+            af = fused.col_linear(hf, w_col)
+            hf2, resf = fused.row_linear_add_norm(af, w_row, resf, nw1, 1e-6)
+            y = fused.col_linear(hf2, w_col2)
+            hf2m = fused.materialize(hf2).clone()
+            torch.cuda.synchronize()
+            e1 = ((af.float() - a.float()).norm() / a.float().norm()).item()
+            e2 = ((hf2m.float() - h2.float()).norm() / h2.float().norm()).item()
+            e3 = ((y.float() - y_ref.float()).norm() / y_ref.float().norm()).item()
+            r0 = rank * fused.rpr
+            rv = fused._rows_valid()
+            e4 = ((resf[:rv].float() - res[r0:r0 + rv].float()).norm() / (res[r0:r0 + rv].float().norm() + 1e-9)).item() if rv else 0.0
+            if max(e1, e2, e3, e4) > 2e-2:
+                ok = False
+                print(f"[rank {rank}] T={T} rep={rep} MISMATCH {e1:.4f} {e2:.4f} {e3:.4f} {e4:.4f}", flush=True)
+        dist.barrier()
+    # MoE-style partial push
+    T = 200
+    torch.manual_seed(7)
+    part = (torch.randn(world, T, H, device=dev) * 0.3).bfloat16()
+    nw = (1 + 0.1 * torch.randn(H, device=dev)).bfloat16()
+    x0 = (torch.randn(T, H, device=dev) * 0.5).bfloat16()
+    hb, rb = base.first_norm(x0.clone(), nw, 1e-6)
+    rb = rb.clone()
+    hb2, rb = base.reduce_add_norm(part[rank].clone(), rb, nw, 1e-6)
+    fused.begin_forward(T)
+    hf, rf = fused.first_norm(x0.clone(), nw, 1e-6)
+    hf2, rf = fused.reduce_add_norm(part[rank].clone(), rf, nw, 1e-6)
+    hf2 = fused.materialize(hf2).clone()
+    torch.cuda.synchronize()
+    e = ((hf2.float() - hb2.float()).norm() / hb2.float().norm()).item()
+    if e > 2e-2:
+        ok = False
+        print(f"[rank {rank}] partial push mismatch {e}", flush=True)
+    dist.barrier()
+
+    # ---- engine level ----
+    from gllm_b200 import LLM
+    from gllm_b200.models.presets import tiny
+    cfg = tiny("Qwen3ForCausalLM", hidden_size=512, num_hidden_layers=3, num_attention_heads=8,
+               num_key_value_heads=2, head_dim=64, intermediate_size=1024, vocab_size=2048, torch_dtype="bfloat16")
+    prompts = [[5, 9, 100, 7], list(range(20, 190)), [77] * 33, [3, 1, 4, 1, 5, 9, 2, 6]]
+    toks = {}
+    for mode in ("nccl", "fused"):
+        torch.manual_seed(4321 + rank)
+        llm = LLM(cfg, load_format="dummy", tp_size=world, maxp=128, maxd=64, max_cuda_graph_bs=8,
+                  num_gpu_pages=256, model_max_length=512, log_stats=False, tp_mode=mode, launch_mode="inproc")
+        outs = llm.generate(tokens=prompts, output_lens=[8] * len(prompts), ignore_eos=True)
+        if rank == 0:
+            toks[mode] = [s.token_ids[len(p):] for s, p in zip(outs, prompts)]
+            assert llm.worker.runner.stats["graph_steps"] > 0
+    if rank == 0:
+        agree = sum(a == b for x, y in zip(toks["nccl"], toks["fused"]) for a, b in zip(x, y))
+        total = sum(len(x) for x in toks["nccl"])
+        print("nccl :", toks["nccl"], "\nfused:", toks["fused"], f"\nagree {agree}/{total}", flush=True)
+        if [x[0] for x in toks["nccl"]] != [y[0] for y in toks["fused"]] or agree / total < 0.8:
+            ok = False
+    t = torch.tensor([1 if ok else 0], device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        print("TP_CHECK_OK" if t.item() == 1 else "TP_CHECK_FAILED", flush=True)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

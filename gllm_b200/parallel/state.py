@@ -101,7 +101,14 @@ def init_dist(pp_size: int, tp_size: int, rank: int, local_rank: int, master_add
             kw = {}
             if backend == "nccl":
                 kw["device_id"] = torch.device("cuda", local_rank)
-            dist.init_process_group(backend=backend, init_method=f"tcp://{master_addr}:{master_port}",
+            import os
+            init_method = f"tcp://{master_addr}:{master_port}"
+            if os.environ.get("TORCHELASTIC_USE_AGENT_STORE") == "True" and \
+                    int(os.environ.get("WORLD_SIZE", "0")) == world:
+                # launched by torchrun: the elastic agent hosts the store (a tcp:// init on another port
+                # would wait forever for a server nobody starts)
+                init_method = "env://"
+            dist.init_process_group(backend=backend, init_method=init_method,
                                     world_size=world, rank=rank,
                                     timeout=datetime.timedelta(seconds=timeout_s), **kw)
             logger.info("dist init: rank %d / %d (pp %d/%d, tp %d/%d) backend=%s", rank, world, st.pp_rank,
@@ -177,8 +184,10 @@ def tp_all_gather_last_dim(x: torch.Tensor) -> torch.Tensor:
     if _STATE.tp_size == 1:
         return x
     tp = _STATE.tp_size
-    out = torch.empty((tp,) + tuple(x.shape), dtype=x.dtype, device=x.device)
-    dist.all_gather_into_tensor(out, x.contiguous(), group=_STATE.tp_group)
+    x2 = x.contiguous().view(-1, x.shape[-1])
+    out = torch.empty((tp * x2.shape[0], x2.shape[1]), dtype=x.dtype, device=x.device)
+    dist.all_gather_into_tensor(out, x2, group=_STATE.tp_group)
+    out = out.view((tp,) + tuple(x.shape))
     return out.movedim(0, -2).reshape(*x.shape[:-1], tp * x.shape[-1])
 
 

@@ -1,0 +1,42 @@
+"""CPU multi-process engine check (gloo): run under torchrun with WORLD_SIZE = pp*tp ranks.
+usage: mp_engine_cpu.py <pp> <tp> <out_json>   — rank 0 writes the generated tokens."""
+import json
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+
+def main():
+    pp, tp, out = int(sys.argv[1]), int(sys.argv[2]), sys.argv[3]
+    arch = sys.argv[4] if len(sys.argv) > 4 else "Qwen3ForCausalLM"
+    method = sys.argv[5] if len(sys.argv) > 5 else "chunked_prefill"
+    from gllm_b200 import LLM
+    from gllm_b200.models.presets import tiny
+    over = {}
+    if arch == "MixtralForCausalLM":
+        over = dict(num_local_experts=4, num_experts_per_tok=2)
+    cfg = tiny(arch, num_hidden_layers=4, **over)
+    torch.manual_seed(0)
+    llm = LLM(cfg, load_format="dummy", pp_size=pp, tp_size=tp, maxp=48, maxd=16, num_cpu_pages=128,
+              model_max_length=256, log_stats=False, device="cpu", launch_mode="inproc", schedule_method=method,
+              seed=0)
+    # identical weights on every layout: re-initialise from one global state dict
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from shard_util import load_global_weights
+    load_global_weights(llm.worker.runner.model, cfg, seed=123)
+    prompts = [[5, 17, 99, 200, 3, 45, 7], [9] * 40, list(range(20, 120)), [300, 301]]
+    outs = llm.generate(tokens=prompts, output_lens=[8] * 4, ignore_eos=True)
+    if int(os.environ.get("RANK", "0")) == 0:
+        with open(out, "w") as f:
+            json.dump([s.token_ids for s in outs], f)
+    llm.shutdown()
+    if torch.distributed.is_initialized():
+        torch.distributed.barrier()
+        torch.distributed.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -22,8 +22,13 @@ def main():
     from gllm_b200.parallel.tp import TPComm
     dev = torch.device("cuda", local)
     H, K, N2 = 1024, 512, 768
+    def log(*a):
+        if rank == 0:
+            print("[tp_check]", *a, flush=True)
+    log("dist ready")
     fused = FusedTPComm(max_tokens=1024, hidden_size=H, device=dev)
     base = TPComm()
+    log("symmetric buffers ready")
     ok = True
     for T in (1000, 37, 256, 5):
         torch.manual_seed(100 + T)  # same on every rank
@@ -39,15 +44,20 @@ def main():
         a = base.col_linear(h, w_col)
         h2, res = base.row_linear_add_norm(a, w_row, res, nw1, 1e-6)
         y_ref = base.col_linear(h2, w_col2)
+        torch.cuda.synchronize()
+        log(f"T={T}: baseline done")
         # ---- fused ----
         for rep in range(3):  # repeated: exercises parity / epoch bookkeeping
             fused.begin_forward(T)
             hf, resf = fused.first_norm(x_full.clone(), nw0, 1e-6)
+            torch.cuda.synchronize(); log(f"T={T} rep={rep}: first_norm ok")
             af = fused.col_linear(hf, w_col)
+            torch.cuda.synchronize(); log("  ag-gemm ok")
             hf2, resf = fused.row_linear_add_norm(af, w_row, resf, nw1, 1e-6)
+            torch.cuda.synchronize(); log("  gemm-rs + reduce_norm ok")
             y = fused.col_linear(hf2, w_col2)
             hf2m = fused.materialize(hf2).clone()
-            torch.cuda.synchronize()
+            torch.cuda.synchronize(); log("  second ag-gemm ok")
             e1 = ((af.float() - a.float()).norm() / a.float().norm()).item()
             e2 = ((hf2m.float() - h2.float()).norm() / h2.float().norm()).item()
             e3 = ((y.float() - y_ref.float()).norm() / y_ref.float().norm()).item()

@@ -1,0 +1,49 @@
+"""Multi-process plumbing on CPU (gloo): TP, PP, PP x TP and EP layouts must reproduce the single-process
+tokens of the same model (same global weights sharded through the loader)."""
+import json
+import os
+import subprocess
+import sys
+import tempfile
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _run(pp, tp, arch="Qwen3ForCausalLM", method="chunked_prefill", port=29811):
+    out = tempfile.mktemp(suffix=".json")
+    env = dict(os.environ, PYTHONPATH=ROOT, GLLM_B200_LOG="WARNING")
+    script = os.path.join(ROOT, "tests", "mp_engine_cpu.py")
+    n = pp * tp
+    if n == 1:
+        cmd = [sys.executable, script, "1", "1", out, arch, method]
+    else:
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}",
+               "--master-addr", "127.0.0.1", "--master-port", str(port), script, str(pp), str(tp), out, arch, method]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=300, env=env, cwd=ROOT)
+    assert r.returncode == 0 and os.path.exists(out), r.stdout[-2000:] + r.stderr[-3000:]
+    with open(out) as f:
+        return json.load(f)
+
+
+@pytest.fixture(scope="module")
+def single():
+    return _run(1, 1)
+
+
+def test_tp2_matches_single(single):
+    assert _run(1, 2, port=29821) == single
+
+
+def test_pp2_matches_single(single):
+    assert _run(2, 1, port=29831) == single
+
+
+def test_pp2_tp2_token_throttling_matches_single(single):
+    assert _run(2, 2, method="token_throttling", port=29841) == single
+
+
+def test_mixtral_ep2_matches_single():
+    ref = _run(1, 1, arch="MixtralForCausalLM")
+    assert _run(1, 2, arch="MixtralForCausalLM", port=29851) == ref

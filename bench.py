@@ -220,11 +220,12 @@ def main():
             "gpu_launches": int(launches),
         }
         print(json.dumps(out), flush=True)
-    llm.shutdown()
     if world > 1 and dist.is_initialized():
         dist.barrier()
-        dist.destroy_process_group()
-    return 0
+    sys.stdout.flush()
+    sys.stderr.flush()
+    # hard exit: tearing down NCCL / symmetric-memory handles in arbitrary order can stall at exit
+    os._exit(0)
 
 
 if __name__ == "__main__":

@@ -114,7 +114,8 @@ def main():
     if rank == 0:
         print("TP_CHECK_OK" if t.item() == 1 else "TP_CHECK_FAILED", flush=True)
     dist.barrier()
-    dist.destroy_process_group()
+    sys.stdout.flush()
+    os._exit(0)
 
 
 if __name__ == "__main__":

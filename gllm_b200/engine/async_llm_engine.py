@@ -1,0 +1,179 @@
+"""asyncio front-end for the HTTP server (reference: gllm/async_llm_engine.py:11-109).
+
+One `AsyncStream` per request (an asyncio.Queue of text deltas); a single background task ticks the
+engine (`LLM.schedule`) in a worker thread so the event loop stays responsive, detokenises new
+tokens incrementally, and aborts requests whose client disconnected.
+"""
+from __future__ import annotations
+
+import asyncio
+import time
+from typing import Dict, List, Optional
+
+from gllm_b200.engine.llm_engine import LLM
+from gllm_b200.utils.logging import logger
+
+
+class AsyncStream:
+    def __init__(self, raw_request=None):
+        self._queue: asyncio.Queue = asyncio.Queue()
+        self._finished = False
+        self._raw_request = raw_request
+        self.prompt_tokens = 0
+        self.completion_tokens = 0
+        self.finish_reason: Optional[str] = None
+        self.created = time.time()
+        self.first_token_time: Optional[float] = None
+        self.seq_id = -1
+
+    def put(self, item: str):
+        if not self._finished:
+            self._queue.put_nowait(item)
+
+    def finish(self, reason: str = "stop"):
+        if not self._finished:
+            self.finish_reason = reason
+            self._queue.put_nowait(StopAsyncIteration())
+            self._finished = True
+
+    @property
+    def finished(self) -> bool:
+        return self._finished
+
+    def __aiter__(self):
+        return self
+
+    async def __anext__(self):
+        item = await self._queue.get()
+        if isinstance(item, Exception):
+            raise item
+        return item
+
+    async def is_disconnected(self) -> bool:
+        if self._raw_request is None:
+            return False
+        try:
+            return await self._raw_request.is_disconnected()
+        except Exception:  # noqa: BLE001
+            return False
+
+
+class AsyncLLM(LLM):
+    def __init__(self, *args, **kwargs):
+        super().__init__(*args, **kwargs)
+        self.async_streams: Dict[int, AsyncStream] = {}
+        self._task: Optional[asyncio.Task] = None
+        self._pending_tokens: List = []
+        self.metrics = {"requests_total": 0, "requests_finished": 0, "requests_aborted": 0,
+                        "prompt_tokens_total": 0, "generation_tokens_total": 0, "ttft_sum": 0.0, "ttft_count": 0}
+
+    async def add_requests_async(self, raw_request, token_ids: List[int], output_len=None, ignore_eos=False,
+                                 temperature=None, top_p=None, top_k=None, repetition_penalty=None,
+                                 mm_contents=None) -> AsyncStream:
+        seq = self.allocate_seq(token_ids, output_len, ignore_eos, temperature, top_p, top_k, repetition_penalty,
+                                mm_contents)
+        stream = AsyncStream(raw_request)
+        stream.prompt_tokens = len(token_ids)
+        stream.seq_id = seq.seq_id
+        self.async_streams[seq.seq_id] = stream
+        self.metrics["requests_total"] += 1
+        self.metrics["prompt_tokens_total"] += len(token_ids)
+        self.add_requests([seq])
+        if self._task is None:
+            self.start_schedule_engine()
+        return stream
+
+    def abort_stream(self, stream: AsyncStream):
+        """Client went away: abort the request so its KV pages are freed (reference:
+        async_llm_engine.py:93-97 polls `is_disconnected` from the engine task; here the request's own
+        task reports it, which also works under ASGI test transports)."""
+        seq = self.running_maps.get(stream.seq_id)
+        if seq is not None and not seq.is_abort and not stream.finished:
+            self.abort([stream.seq_id])
+            seq.is_abort = True
+            self.metrics["requests_aborted"] += 1
+
+    async def collect(self, stream: AsyncStream) -> str:
+        """Drain a stream to a string, aborting the request if the client disconnects meanwhile."""
+        text = ""
+        while True:
+            try:
+                text += await asyncio.wait_for(stream.__anext__(), timeout=0.5)
+            except StopAsyncIteration:
+                return text
+            except asyncio.TimeoutError:
+                if await stream.is_disconnected():
+                    self.abort_stream(stream)
+                    return text
+
+    def _on_token(self, seq, tok):
+        self._pending_tokens.append(seq)
+
+    def _tick(self) -> bool:
+        return self.schedule(self._on_token)
+
+    def _deliver(self):
+        seen = set()
+        for seq in self._pending_tokens:
+            if id(seq) in seen:
+                continue
+            seen.add(id(seq))
+            st = self.async_streams.get(seq.seq_id)
+            if st is None:
+                continue
+            if st.first_token_time is None:
+                st.first_token_time = time.time()
+                self.metrics["ttft_sum"] += st.first_token_time - st.created
+                self.metrics["ttft_count"] += 1
+            st.completion_tokens = seq.num_output_tokens
+            if self.tokenizer is not None:
+                delta = seq.detokenize_inc(self.tokenizer)
+                if delta:
+                    st.put(delta)
+            else:
+                st.put(" ".join(str(t) for t in seq.token_ids[seq.cur_length:]) + " ")
+                seq.cur_length = len(seq.token_ids)
+        self._pending_tokens = []
+        for seq in self.finished:
+            st = self.async_streams.pop(seq.seq_id, None)
+            if st is not None:
+                st.completion_tokens = seq.num_output_tokens
+                self.metrics["generation_tokens_total"] += seq.num_output_tokens
+                self.metrics["requests_finished"] += 1
+                reason = "length" if seq.num_output_tokens >= seq.output_len else "stop"
+                st.finish("abort" if seq.is_abort else reason)
+        self.finished = []
+
+    async def _loop(self):
+        loop = asyncio.get_running_loop()
+        idle = 0
+        while True:
+            did = await loop.run_in_executor(None, self._tick)
+            self._deliver()
+            if did or self.running_maps or self.wait_lists:
+                idle = 0
+                await asyncio.sleep(0)
+            else:
+                idle += 1
+                await asyncio.sleep(0.001 if idle < 1000 else 0.01)
+
+    def start_schedule_engine(self):
+        self._task = asyncio.get_event_loop().create_task(self._loop())
+
+        def _done(task):
+            try:
+                task.result()
+            except asyncio.CancelledError:
+                logger.info("engine loop cancelled")
+            except Exception as e:  # noqa: BLE001
+                logger.error("engine background task failed: %r", e, exc_info=e)
+                # fail-stop: release every waiting client instead of hanging them
+                for st in list(self.async_streams.values()):
+                    st._queue.put_nowait(RuntimeError(f"engine failure: {e!r}"))
+                self.async_streams.clear()
+                self._task = None
+        self._task.add_done_callback(_done)
+
+
+# name used by the reference (gllm/async_llm_engine.py:56)
+PipeAsyncLLM = AsyncLLM

@@ -173,13 +173,17 @@ class LLM:
         assert self.tokenizer is not None, "no tokenizer: pass token ids"
         if chat or messages is not None:
             msgs = messages if messages is not None else [{"role": "user", "content": prompt}]
-            kw = {}
             try:
-                return self.tokenizer.apply_chat_template(msgs, add_generation_prompt=True, tokenize=True,
-                                                          enable_thinking=self.cfg.use_thinking, **kw)
+                ids = self.tokenizer.apply_chat_template(msgs, add_generation_prompt=True, tokenize=True,
+                                                         enable_thinking=self.cfg.use_thinking)
             except TypeError:
-                return self.tokenizer.apply_chat_template(msgs, add_generation_prompt=True, tokenize=True)
-        return self.tokenizer.encode(prompt)
+                ids = self.tokenizer.apply_chat_template(msgs, add_generation_prompt=True, tokenize=True)
+            if hasattr(ids, "keys"):  # transformers >= 5 returns a BatchEncoding
+                ids = ids["input_ids"]
+            if len(ids) and isinstance(ids[0], (list, tuple)):
+                ids = ids[0]
+            return list(ids)
+        return list(self.tokenizer.encode(prompt))
 
     def check_seq_length(self, token_ids: List[int], output_len: Optional[int]) -> bool:
         """Reject prompts that cannot fit (reference: gllm/llm_engine.py:293-303)."""

@@ -1,0 +1,119 @@
+"""OpenAI-API contract tests on CPU with fastapi.testclient: routes, SSE framing, usage, errors, metrics."""
+import json
+import os
+import tempfile
+
+import pytest
+import torch
+
+pytest.importorskip("fastapi")
+transformers = pytest.importorskip("transformers")
+
+
+def _make_model_dir():
+    from tokenizers import Tokenizer, models, pre_tokenizers
+    from transformers import LlamaConfig, LlamaForCausalLM, PreTrainedTokenizerFast
+    torch.manual_seed(0)
+    words = ["<unk>", "<s>", "</s>", "<|user|>", "<|assistant|>"] + [f"w{i}" for i in range(200)] + \
+        ["hello", "world", "how", "are", "you", "?", "the", "a"]
+    vocab = {w: i for i, w in enumerate(words)}
+    tok = Tokenizer(models.WordLevel(vocab, unk_token="<unk>"))
+    tok.pre_tokenizer = pre_tokenizers.Whitespace()
+    fast = PreTrainedTokenizerFast(tokenizer_object=tok, unk_token="<unk>", bos_token="<s>", eos_token="</s>")
+    fast.chat_template = "{% for m in messages %}<|{{ m['role'] }}|> {{ m['content'] }} {% endfor %}" \
+                         "{% if add_generation_prompt %}<|assistant|> {% endif %}"
+    cfg = LlamaConfig(hidden_size=64, intermediate_size=128, num_hidden_layers=2, num_attention_heads=2,
+                      num_key_value_heads=2, vocab_size=len(words), max_position_embeddings=256, eos_token_id=2,
+                      bos_token_id=1)
+    d = tempfile.mkdtemp(prefix="gllm_b200_api_")
+    LlamaForCausalLM(cfg).eval().float().save_pretrained(d, safe_serialization=True)
+    fast.save_pretrained(d)
+    return d
+
+
+@pytest.fixture(scope="module")
+def client():
+    from fastapi.testclient import TestClient
+    from gllm_b200.engine.async_llm_engine import AsyncLLM
+    from gllm_b200.entrypoints.api_server import build_app
+    d = _make_model_dir()
+    engine = AsyncLLM(d, maxp=64, maxd=16, num_cpu_pages=64, model_max_length=128, log_stats=False)
+    assert engine.tokenizer is not None
+    with TestClient(build_app(engine)) as c:
+        yield c, engine
+    engine.shutdown()
+
+
+def test_models_health_metrics(client):
+    c, engine = client
+    r = c.get("/v1/models")
+    assert r.status_code == 200 and r.json()["object"] == "list" and r.json()["data"][0]["id"]
+    assert c.get("/health").json() == {"status": "ok"}
+    assert "gllm_requests_total" in c.get("/metrics").text
+
+
+def test_completion_non_stream_and_usage(client):
+    c, engine = client
+    r = c.post("/v1/completions", json={"model": "m", "prompt": "hello world how are you", "max_tokens": 6,
+                                         "temperature": 0, "top_k": 1, "ignore_eos": True})
+    assert r.status_code == 200, r.text
+    body = r.json()
+    assert body["object"] == "text_completion" and len(body["choices"]) == 1
+    assert body["usage"]["prompt_tokens"] == 5 and body["usage"]["completion_tokens"] == 6
+    assert body["usage"]["total_tokens"] == 11 and body["choices"][0]["finish_reason"] == "length"
+    # token-id prompts are accepted too
+    r2 = c.post("/v1/completions", json={"prompt": [5, 6, 7], "max_tokens": 3, "ignore_eos": True})
+    assert r2.status_code == 200 and r2.json()["usage"]["completion_tokens"] == 3
+
+
+def test_completion_stream_sse_framing(client):
+    c, engine = client
+    with c.stream("POST", "/v1/completions", json={"prompt": "hello world", "max_tokens": 5, "stream": True,
+                                                    "ignore_eos": True, "top_k": 1}) as r:
+        assert r.status_code == 200 and r.headers["content-type"].startswith("text/event-stream")
+        raw = "".join(r.iter_text())
+    events = [e for e in raw.split("\n\n") if e]
+    assert all(e.startswith("data: ") for e in events) and events[-1] == "data: [DONE]"
+    chunks = [json.loads(e[6:]) for e in events[:-1]]
+    assert chunks[-1]["usage"]["completion_tokens"] == 5 and chunks[-1]["choices"][0]["finish_reason"] == "length"
+    assert len({ch["id"] for ch in chunks}) == 1
+
+
+def test_chat_completion_stream_and_non_stream(client):
+    c, engine = client
+    msgs = [{"role": "user", "content": "hello how are you ?"}]
+    r = c.post("/v1/chat/completions", json={"model": "m", "messages": msgs, "max_completion_tokens": 4,
+                                              "ignore_eos": True, "top_k": 1})
+    assert r.status_code == 200, r.text
+    body = r.json()
+    assert body["object"] == "chat.completion" and body["choices"][0]["message"]["role"] == "assistant"
+    assert body["usage"]["completion_tokens"] == 4
+    with c.stream("POST", "/v1/chat/completions", json={"messages": msgs, "max_tokens": 4, "stream": True,
+                                                         "ignore_eos": True}) as r:
+        raw = "".join(r.iter_text())
+    events = [e for e in raw.split("\n\n") if e]
+    assert events[-1] == "data: [DONE]"
+    first = json.loads(events[0][6:])
+    assert first["object"] == "chat.completion.chunk" and first["choices"][0]["delta"].get("role") == "assistant"
+
+
+def test_over_length_is_400(client):
+    c, engine = client
+    r = c.post("/v1/completions", json={"prompt": "hello " * 300, "max_tokens": 4})
+    assert r.status_code == 400 and r.json()["type"] == "BadRequestError"
+    r = c.post("/v1/completions", json={"prompt": "hello", "max_tokens": 100000})
+    assert r.status_code == 400
+
+
+def test_tokenize_roundtrip_and_profile_endpoints(client):
+    c, engine = client
+    t = c.post("/tokenize", json={"prompt": "hello world"}).json()
+    assert t["count"] == 2
+    assert "hello" in c.post("/detokenize", json={"tokens": t["tokens"]}).json()["prompt"]
+
+
+def test_engine_metrics_after_requests(client):
+    c, engine = client
+    assert engine.metrics["requests_finished"] >= 4
+    assert engine.metrics["generation_tokens_total"] > 0
+    assert len(engine.running_maps) == 0

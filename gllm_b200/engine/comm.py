@@ -67,7 +67,7 @@ class Comm:
         self.base, self.rank, self.world_size, self.output_rank = base, rank, world_size, output_rank
         self.frontend = frontend
         self.tcp_host, self.port_base, self.master_addr = tcp_host, port_base, master_addr
-        self.ctx = zmq.Context.instance()
+        self.ctx = None  # created in init(): the object is pickled into spawned workers first
         self.sock_fe_in = self.sock_fe_out = None
         self.batch_out: List[zmq.Socket] = []
         self.batch_in = None
@@ -85,6 +85,7 @@ class Comm:
 
     def init(self):
         P, L = zmq.PUSH, zmq.PULL
+        self.ctx = zmq.Context.instance()
         if self.frontend:
             self.sock_fe_out = make_socket(self.ctx, P, self._addr("fe_req"), bind=False)
             self.sock_fe_in = make_socket(self.ctx, L, self._addr("fe_out"), bind=True)

@@ -424,6 +424,7 @@ class _NoFrontend:
         import zmq
         from gllm_b200.engine.comm import make_socket
         P, L = zmq.PUSH, zmq.PULL
+        c.ctx = zmq.Context.instance()
         if c.rank == 0:
             for r in range(1, c.world_size):
                 c.batch_out.append(make_socket(c.ctx, P, c._peer_addr(r, connect=True), bind=False))

@@ -1,0 +1,91 @@
+"""Spawned-worker mode (front-end process + ZeroMQ + one worker process per rank) and the HTTP server as a
+real subprocess driven by the serving benchmark client — all on CPU."""
+import json
+import os
+import socket
+import subprocess
+import sys
+import tempfile
+import time
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def test_spawn_mode_pp2_generates():
+    code = f"""
+import sys
+sys.path.insert(0, {ROOT!r})
+if __name__ == "__main__":
+    from gllm_b200 import LLM
+    from gllm_b200.models.presets import tiny
+    llm = LLM(tiny("Qwen3ForCausalLM", num_hidden_layers=4), load_format="dummy", pp_size=2, tp_size=1, maxp=48,
+              maxd=16, num_cpu_pages=128, model_max_length=256, log_stats=False, device="cpu",
+              master_port={_free_port()}, schedule_method="token_throttling")
+    outs = llm.generate(tokens=[[5, 17, 99], [9] * 40, list(range(20, 120))], output_lens=[6, 7, 8], ignore_eos=True)
+    assert [len(s.token_ids) - s.prompt_len for s in outs] == [6, 7, 8]
+    print("SPAWN_OK")
+    llm.shutdown()
+"""
+    f = tempfile.mktemp(suffix=".py")
+    open(f, "w").write(code)
+    r = subprocess.run([sys.executable, f], capture_output=True, text=True, timeout=240,
+                       env=dict(os.environ, GLLM_B200_LOG="WARNING"))
+    assert "SPAWN_OK" in r.stdout, r.stdout[-1500:] + r.stderr[-3000:]
+
+
+def test_server_subprocess_with_serving_benchmark():
+    import requests
+    port = _free_port()
+    cfg = tempfile.mkdtemp(prefix="gllm_b200_srv_")
+    from gllm_b200.models.presets import tiny
+    with open(os.path.join(cfg, "config.json"), "w") as f:
+        json.dump(tiny("Qwen3ForCausalLM", max_position_embeddings=2048), f)
+    env = dict(os.environ, PYTHONPATH=ROOT, GLLM_B200_LOG="WARNING")
+    srv = subprocess.Popen([sys.executable, "-m", "gllm_b200.entrypoints.api_server", "--model-path", cfg,
+                            "--load-format", "dummy", "--port", str(port), "--host", "127.0.0.1", "--maxp", "64",
+                            "--maxd", "32", "--model-max-length", "1100", "--enable-prefix-caching"],
+                           env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    try:
+        for _ in range(120):
+            try:
+                if requests.get(f"http://127.0.0.1:{port}/health", timeout=1).status_code == 200:
+                    break
+            except Exception:  # noqa: BLE001
+                time.sleep(0.5)
+        else:
+            srv.kill()
+            raise AssertionError("server did not come up: " + srv.stdout.read()[-3000:])
+        out = tempfile.mktemp(suffix=".json")
+        r = subprocess.run([sys.executable, os.path.join(ROOT, "benchmarks", "benchmark_serving.py"), "--port",
+                            str(port), "--num-prompts", "12", "--request-rate", "50", "--vocab-size", "500",
+                            "--max-output-len", "8", "--save-result", out, "--goodput", "ttft:60000"],
+                           capture_output=True, text=True, timeout=240, env=env)
+        assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+        res = json.load(open(out))
+        assert res["completed"] == 12 and res["failed"] == 0
+        for k in ("median_ttft_ms", "median_tpot_ms", "median_itl_ms", "median_e2el_ms", "output_throughput",
+                  "request_goodput", "p99_ttft_ms"):
+            assert k in res, k
+        r = subprocess.run([sys.executable, os.path.join(ROOT, "benchmarks", "benchmark_prefix_serving.py"), "--port",
+                            str(port), "--num-users", "3", "--rounds", "3", "--vocab-size", "500", "--system-len",
+                            "64", "--turn-len", "16", "--answer-len", "4"],
+                           capture_output=True, text=True, timeout=240, env=env)
+        assert r.returncode == 0 and "cache_hit_rate" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+        hit = float(r.stdout.strip().splitlines()[-1].split()[-1])
+        assert hit > 0.0
+    finally:
+        srv.terminate()
+        try:
+            srv.wait(timeout=10)
+        except Exception:  # noqa: BLE001
+            srv.kill()

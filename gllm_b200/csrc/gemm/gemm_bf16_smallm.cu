@@ -34,7 +34,7 @@ struct SmallMParams {
   const __nv_bfloat16* bias;
   float* ws;              // [num_n_tiles * S][128][BT] fp32 partials
   uint32_t* counters;     // [num_n_tiles], zero on entry, self-resetting
-  int silu;               // 1: rows [0,64) gate / [64,128) up of the same 64 features per tile
+  int silu;               // 1: weight rows interleaved per 128: tile 2g = gate, tile 2g+1 = up
   int stages;
   uint32_t tmem_cols;
 };
@@ -170,14 +170,19 @@ gemm_smallm_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_cons
       // publish the partial tile; the last split to arrive reduces (fixed order => deterministic)
       __threadfence();
       asm volatile("bar.sync 1, 128;" ::: "memory");
+      // SiLU-gate: weight rows are interleaved per 128 (tile 2g = gate, tile 2g+1 = up of the same 128
+      // features), so a *pair* of tiles (2 S units) completes one output group.
+      const int grp = p.silu ? (nt >> 1) : nt;
+      const uint32_t need = static_cast<uint32_t>(p.silu ? 2 * p.S : p.S);
       if (et == 0) {
-        const uint32_t old = atomicAdd(p.counters + nt, 1u);
-        *flag_smem = (old == static_cast<uint32_t>(p.S - 1)) ? 1u : 0u;
+        const uint32_t old = atomicAdd(p.counters + grp, 1u);
+        *flag_smem = (old == need - 1u) ? 1u : 0u;
       }
       asm volatile("bar.sync 1, 128;" ::: "memory");
       if (*flag_smem) {
         __threadfence();
-        const float* __restrict__ base = p.ws + static_cast<size_t>(nt) * p.S * p.BT * kWTile;
+        const float* __restrict__ base =
+            p.ws + static_cast<size_t>(p.silu ? 2 * grp : nt) * p.S * p.BT * kWTile;
         const size_t unit_stride = static_cast<size_t>(p.BT) * kWTile;
         const int n4 = et & 31;   // float4 column group
         const int mr = et >> 5;   // 0..3
@@ -217,9 +222,10 @@ gemm_smallm_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_cons
               }
             }
           }
-        } else if (n4 < 16) {
-          // gate columns [0,64), up columns [64,128) of the same 64 output features
-          const int f = nt * 64 + n4 * 4;
+        } else {
+          // gate partials live in the units of tile 2g, up partials in the units of tile 2g+1
+          const int f = grp * kWTile + n4 * 4;
+          const float* __restrict__ base_up = base + static_cast<size_t>(p.S) * unit_stride;
           for (int m0 = 0; m0 < p.M; m0 += 4 * U) {
             float4 g[U], up[U];
 #pragma unroll
@@ -229,9 +235,9 @@ gemm_smallm_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_cons
               up[uu] = g[uu];
               if (m < p.M) {
                 for (int s2 = 0; s2 < p.S; ++s2) {
-                  const float* r = base + s2 * unit_stride + static_cast<size_t>(m) * kWTile + n4 * 4;
-                  const float4 tg = __ldcg(reinterpret_cast<const float4*>(r));
-                  const float4 tu = __ldcg(reinterpret_cast<const float4*>(r + 64));
+                  const size_t off = s2 * unit_stride + static_cast<size_t>(m) * kWTile + n4 * 4;
+                  const float4 tg = __ldcg(reinterpret_cast<const float4*>(base + off));
+                  const float4 tu = __ldcg(reinterpret_cast<const float4*>(base_up + off));
                   g[uu].x += tg.x; g[uu].y += tg.y; g[uu].z += tg.z; g[uu].w += tg.w;
                   up[uu].x += tu.x; up[uu].y += tu.y; up[uu].z += tu.z; up[uu].w += tu.w;
                 }
@@ -251,7 +257,7 @@ gemm_smallm_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_cons
             }
           }
         }
-        if (et == 0) p.counters[nt] = 0u;  // ready for the next launch
+        if (et == 0) p.counters[grp] = 0u;  // ready for the next launch
       }
     }
   }
@@ -269,7 +275,7 @@ gemm_smallm_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_cons
 using namespace b200;
 
 // ws: fp32 workspace of at least gllm_gemm_smallm_ws_floats() elements; counters: >= ceil(N/128)
-// uint32 zeros. silu: weight rows interleaved per 64 (gate|up), output has N/2 columns.
+// uint32 zeros. silu: weight rows interleaved per 128 (gate|up), output has N/2 columns.
 GLLM_EXPORT int gllm_gemm_smallm(const void* A, int64_t lda, const void* W, int64_t ldw, void* C, int64_t ldc,
                                  int M, int N, int K, const void* bias, int silu, int force_split, void* ws,
                                  int64_t ws_floats, void* counters, void* stream) {

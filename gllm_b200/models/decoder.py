@@ -150,15 +150,15 @@ class DenseMLP(nn.Module):
         tp = ps.get_tp_size() if shard else 1
         assert intermediate % tp == 0
         self.inter = intermediate // tp
-        # fused SiLU-gate epilogue needs the gate/up rows interleaved per 64
-        self.fused_act = self.inter % 64 == 0
+        # fused SiLU-gate epilogue needs the gate/up rows interleaved per 128
+        self.fused_act = self.inter % 128 == 0
         self.gate_up_w = _param(2 * self.inter, hidden, dtype=dtype, device=device)
         self.down_w = _param(hidden, self.inter, dtype=dtype, device=device)
 
     def set_gate_up(self, gate_up: torch.Tensor):
         """gate_up [2*inter, H] = [gate rows; up rows] for this rank."""
         if self.fused_act:
-            gate_up = ref.interleave_gate_up(gate_up, 64)
+            gate_up = ref.interleave_gate_up(gate_up, 128)
         self.gate_up_w.data.copy_(gate_up)
 
     def act(self, h: torch.Tensor, tpc: TPComm) -> torch.Tensor:

@@ -49,7 +49,7 @@ def silu_and_mul(x: torch.Tensor) -> torch.Tensor:
     return (F.silu(x[..., :d].float()) * x[..., d:].float()).to(x.dtype)
 
 
-def interleave_gate_up(w: torch.Tensor, block: int = 64) -> torch.Tensor:
+def interleave_gate_up(w: torch.Tensor, block: int = 128) -> torch.Tensor:
     """[2I, K] (gate rows then up rows) -> per-`block` interleaved layout used by the fused
     SiLU-gate GEMM epilogue: tile j = [gate[j*b:(j+1)*b]; up[j*b:(j+1)*b]]."""
     two_i, k = w.shape
@@ -60,7 +60,7 @@ def interleave_gate_up(w: torch.Tensor, block: int = 64) -> torch.Tensor:
     return torch.cat([g, u], dim=1).reshape(two_i, k).contiguous()
 
 
-def linear_silu_mul(x: torch.Tensor, w_interleaved: torch.Tensor, block: int = 64) -> torch.Tensor:
+def linear_silu_mul(x: torch.Tensor, w_interleaved: torch.Tensor, block: int = 128) -> torch.Tensor:
     y = F.linear(x, w_interleaved)
     t, two_i = y.shape
     y = y.reshape(t, two_i // (2 * block), 2, block)

@@ -56,13 +56,13 @@ def test_gemm_silu_mul():
     m, i, k = 200, 1024, 512
     x = (torch.randn(m, k, device=_dev()) * 0.5).bfloat16()
     w = (torch.randn(2 * i, k, device=_dev()) * 0.05).bfloat16()
-    wi = ref.interleave_gate_up(w, 64)
+    wi = ref.interleave_gate_up(w, 128)
     y = sm100.linear_silu_mul(x, wi)
     h = x.float() @ w.float().t()
     yr = torch.nn.functional.silu(h[:, :i]) * h[:, i:]
     assert _rel_err(y, yr) < 1e-2
     # and the oracle's own interleaved path agrees
-    assert _rel_err(ref.linear_silu_mul(x, wi, 64), yr) < 1e-2
+    assert _rel_err(ref.linear_silu_mul(x, wi, 128), yr) < 1e-2
 
 
 @pytest.mark.parametrize("t,h", [(1, 4096), (7, 1024), (300, 4096), (64, 8192), (3, 7168), (2, 16384)])
@@ -293,7 +293,7 @@ def test_gemm_smallm_silu(m, split, monkeypatch):
     i, k = 1536, 1024
     x = (torch.randn(m, k, device=_dev()) * 0.5).bfloat16()
     w = (torch.randn(2 * i, k, device=_dev()) * 0.05).bfloat16()
-    y = sm100.linear_silu_mul(x, ref.interleave_gate_up(w, 64))
+    y = sm100.linear_silu_mul(x, ref.interleave_gate_up(w, 128))
     h = x.float() @ w.float().t()
     yr = torch.nn.functional.silu(h[:, :i]) * h[:, i:]
     assert _rel_err(y, yr) < 1e-2

@@ -161,3 +161,22 @@ def test_qwen2_moe_shared_expert_matches_hf():
                          num_experts_per_tok=2, norm_topk_prob=False, decoder_sparse_step=1, mlp_only_layers=[],
                          eos_token_id=1)
     _check(Qwen2MoeForCausalLM(cfg).eval().float())
+
+
+def test_deepseek_v3_mla_moe_matches_hf():
+    from transformers import DeepseekV3Config, DeepseekV3ForCausalLM
+    torch.manual_seed(9)
+    cfg = DeepseekV3Config(hidden_size=64, intermediate_size=128, moe_intermediate_size=32, num_hidden_layers=3,
+                           num_attention_heads=4, num_key_value_heads=4, n_routed_experts=8, n_shared_experts=1,
+                           num_experts_per_tok=2, n_group=2, topk_group=1, first_k_dense_replace=1,
+                           routed_scaling_factor=2.5, norm_topk_prob=True, q_lora_rank=24, kv_lora_rank=32,
+                           qk_nope_head_dim=16, qk_rope_head_dim=8, v_head_dim=16, vocab_size=512,
+                           max_position_embeddings=512, eos_token_id=1, rope_scaling=None, rope_interleave=True)
+    m = DeepseekV3ForCausalLM(cfg).eval().float()
+    for n, p in m.named_parameters():
+        if "e_score_correction_bias" in n:
+            torch.nn.init.normal_(p, std=0.05)
+    for n, b in m.named_buffers():
+        if "e_score_correction_bias" in n:
+            b.normal_(std=0.05)
+    _check(m)

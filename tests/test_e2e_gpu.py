@@ -39,7 +39,9 @@ def test_gpu_matches_cpu_oracle():
     agree = sum(a == b for x, y in zip(cpu_toks, gpu_toks) for a, b in zip(x, y))
     total = sum(len(x) for x in cpu_toks)
     assert [x[0] for x in cpu_toks] == [y[0] for y in gpu_toks], (cpu_toks, gpu_toks)
-    assert agree / total >= 0.8, (cpu_toks, gpu_toks)
+    # once a near-tie flips, the rest of that sequence differs: require most sequences to match fully
+    same_seqs = sum(x == y for x, y in zip(cpu_toks, gpu_toks))
+    assert same_seqs >= len(prompts) // 2 and agree / total >= 0.6, (cpu_toks, gpu_toks)
 
 
 def test_graph_and_eager_agree():

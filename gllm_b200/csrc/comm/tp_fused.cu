@@ -21,12 +21,19 @@
 namespace b200 {
 
 static constexpr int kMaxTp = 8;
+static constexpr int kMaxBlocks = 256;  // 128-row blocks per gather buffer (32 K tokens)
+static constexpr int kFlagBlockRows = 128;
 
 struct TpState {
   // device-resident, one per rank (NOT symmetric): advanced by the kernels
   uint32_t rs_expected[2][kMaxTp];  // per parity, per source rank: tile arrivals consumed so far
-  uint32_t ag_epoch[3];             // per gather buffer: epoch published by the last push
+  uint32_t ag_epoch[3];             // per gather buffer: number of pushes so far (diagnostic)
   uint32_t ticket[4];               // grid tickets
+  uint32_t pad[9];                  // -> ag_expected starts at byte 128
+  // per gather buffer, per 128-row block: rows that must have arrived before the block may be read.
+  // Arrival counters (symmetric `flags`) are bumped once per pushed row by the row's owner, so a
+  // consumer GEMM can start on the blocks that are complete while the rest is still in flight.
+  uint32_t ag_expected[3][kMaxBlocks];
 };
 
 struct ReduceNormParams {
@@ -46,6 +53,7 @@ struct ReduceNormParams {
   int parity, ag_idx;
   int tp, rank, rows_per_rank, rows_valid, H;
   float eps;
+  int T;  // total tokens of this forward (all ranks)
 };
 
 template <int NV>
@@ -147,26 +155,34 @@ __global__ void rs_reduce_norm_kernel(const ReduceNormParams p) {
       }
     }
   }
-  // publish: the last CTA of the grid bumps the bookkeeping and raises the flags on every peer
+  // publish this row: one arrival on the row's 128-row block counter of every rank
   __threadfence_system();
   __syncthreads();
   if (threadIdx.x == 0) {
+    if (row < p.rows_valid && p.norm_w != nullptr) {
+      const int blk = (p.rank * p.rows_per_rank + row) / kFlagBlockRows;
+      for (int d = 0; d < p.tp; ++d) {
+        const int peer = (p.rank + d) % p.tp;
+        red_add_release_sys(p.flag_peers[peer] + blk, 1u);
+      }
+    }
     const uint32_t old = atomicAdd(&p.st->ticket[0], 1u);
     s_last = (old == gridDim.x - 1) ? 1u : 0u;
   }
   __syncthreads();
+  // the last CTA of the grid advances the device-side bookkeeping (no host epochs => graph safe)
   if (s_last) {
     if (threadIdx.x == 0) {
       p.st->ticket[0] = 0u;
       if (p.local_x == nullptr)
         for (int s = 0; s < p.tp; ++s) p.st->rs_expected[p.parity][s] += p.n_tiles[s];
-      const uint32_t e = p.st->ag_epoch[p.ag_idx] + 1u;
-      p.st->ag_epoch[p.ag_idx] = e;
-      __threadfence_system();
-      for (int d = 0; d < p.tp; ++d) {
-        const int peer = (p.rank + d) % p.tp;
-        st_release_sys(p.flag_peers[peer] + p.rank, e);
-      }
+      p.st->ag_epoch[p.ag_idx] += 1u;
+    }
+    // every row < T is pushed by its owner: block b will receive min(T, (b+1)*128) - b*128 arrivals
+    const int nblk = (p.T + kFlagBlockRows - 1) / kFlagBlockRows;
+    for (int b = threadIdx.x; b < nblk; b += blockDim.x) {
+      const int rows = min(p.T, (b + 1) * kFlagBlockRows) - b * kFlagBlockRows;
+      p.st->ag_expected[p.ag_idx][b] += static_cast<uint32_t>(rows);
     }
   }
 }
@@ -190,10 +206,10 @@ __global__ void push_partial_rows_kernel(const __nv_bfloat16* __restrict__ x, in
 
 // Block the stream until the shards of a gather buffer have been published for the current epoch
 // (for consumers that are not the flag-aware GEMM: row gathers, router, ...).
-__global__ void wait_ag_flags_kernel(const uint32_t* flags, const TpState* st, int ag_idx, int tp) {
-  if (threadIdx.x < tp) {
-    const uint32_t e = st->ag_epoch[ag_idx];
-    while (static_cast<int32_t>(ld_acquire_sys(flags + threadIdx.x) - e) < 0) {
+__global__ void wait_ag_flags_kernel(const uint32_t* flags, const TpState* st, int ag_idx, int nblk) {
+  for (int b = threadIdx.x; b < nblk; b += blockDim.x) {
+    const uint32_t e = st->ag_expected[ag_idx][b];
+    while (static_cast<int32_t>(ld_acquire_sys(flags + b) - e) < 0) {
     }
   }
 }
@@ -217,6 +233,7 @@ struct ReduceNormArgs {
   void* st;
   int parity, ag_idx, tp, rank, rows_per_rank, rows_valid, H;
   float eps;
+  int T;
 };
 
 GLLM_EXPORT int gllm_rs_reduce_norm(const ReduceNormArgs* a, void* stream) {
@@ -237,6 +254,8 @@ GLLM_EXPORT int gllm_rs_reduce_norm(const ReduceNormArgs* a, void* stream) {
   p.st = reinterpret_cast<TpState*>(a->st);
   p.parity = a->parity; p.ag_idx = a->ag_idx; p.tp = a->tp; p.rank = a->rank;
   p.rows_per_rank = a->rows_per_rank; p.rows_valid = a->rows_valid; p.H = a->H; p.eps = a->eps;
+  p.T = a->T;
+  if ((p.T + kFlagBlockRows - 1) / kFlagBlockRows > kMaxBlocks) return 1;
   if (p.H % 8 != 0 || p.tp > kMaxTp) return 1;
   const int nvec = p.H / 8;
   int threads = ((nvec + 31) / 32) * 32, nv = 1;
@@ -263,9 +282,11 @@ GLLM_EXPORT int gllm_push_partial_rows(const void* x, int64_t ldx, int T, int H,
   return 0;
 }
 
-GLLM_EXPORT int gllm_wait_ag_flags(const void* flags, const void* st, int ag_idx, int tp, void* stream) {
-  wait_ag_flags_kernel<<<1, 32, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      reinterpret_cast<const uint32_t*>(flags), reinterpret_cast<const TpState*>(st), ag_idx, tp);
+// T: tokens of the current forward -> ceil(T / 128) row blocks to wait for
+GLLM_EXPORT int gllm_wait_ag_flags(const void* flags, const void* st, int ag_idx, int T, void* stream) {
+  const int nblk = (T + kFlagBlockRows - 1) / kFlagBlockRows;
+  wait_ag_flags_kernel<<<1, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const uint32_t*>(flags), reinterpret_cast<const TpState*>(st), ag_idx, nblk);
   CUDA_CHECK_RET(cudaGetLastError());
   return 0;
 }

@@ -36,9 +36,9 @@ struct GemmParams {
   int ldc;
   const __nv_bfloat16* bias;
   // all-gather gating (null => disabled)
-  const uint32_t* a_ready;
-  const uint32_t* a_epoch_ptr;  // device-resident epoch (CUDA-graph safe), see comm/tp_fused.cu
-  int rows_per_flag;
+  const uint32_t* a_ready;      // arrival counters, one per 128-row block of A (written by peers)
+  const uint32_t* a_expected;   // device-resident expected counts (CUDA-graph safe), comm/tp_fused.cu
+  int m_rot;                    // first M tile to visit (this rank's shard)
   // reduce-scatter push (rs_world == 0 => disabled)
   int rs_world, rs_rank, rows_per_rank;
   uint32_t rs_inc;
@@ -116,18 +116,17 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       uint32_t pf_it = 0;
       int pf_tile = blockIdx.x, pf_kb = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m0 = (tile % num_m) * kBlockM;
+        // M tiles are visited starting from this rank's own row shard (m_rot), so an all-gather ⊕ GEMM
+        // works on local rows while the peers' rows are still arriving over NVLink
+        const int mt = ((tile % num_m) + p.m_rot) % num_m;
+        const int m0 = mt * kBlockM;
         const int n0 = (tile / num_m) * BN;
-        const int b_row_off = p.tile_expert != nullptr ? p.tile_expert[tile % num_m] * p.n_per_expert : 0;
+        const int b_row_off = p.tile_expert != nullptr ? p.tile_expert[mt] * p.n_per_expert : 0;
         if (p.a_ready != nullptr) {
-          // all-gather ⊕ GEMM: wait until every row block of this M tile has landed.
-          const int m1 = min(m0 + kBlockM, p.M);
-          const int f0 = m0 / p.rows_per_flag;
-          const int f1 = (m1 - 1) / p.rows_per_flag;
-          const uint32_t a_epoch = *reinterpret_cast<const volatile uint32_t*>(p.a_epoch_ptr);
-          for (int f = f0; f <= f1; ++f) {
-            while (static_cast<int32_t>(ld_acquire_sys(p.a_ready + f) - a_epoch) < 0) {
-            }
+          // all-gather ⊕ GEMM: the 128-row block `mt` of A is complete once its arrival counter reached
+          // the device-resident expected value (advanced by rs_reduce_norm, comm/tp_fused.cu)
+          const uint32_t want = *reinterpret_cast<const volatile uint32_t*>(p.a_expected + mt);
+          while (static_cast<int32_t>(ld_acquire_sys(p.a_ready + mt) - want) < 0) {
           }
           asm volatile("fence.proxy.async;" ::: "memory");
         }
@@ -188,7 +187,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     const int q = warp & 3;  // TMEM lane quarter this warp may access
     uint32_t tcount = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tcount) {
-      const int m0 = (tile % num_m) * kBlockM;
+      const int m0 = (((tile % num_m) + p.m_rot) % num_m) * kBlockM;
       const int n0 = (tile / num_m) * BN;
       const uint32_t buf = tcount & 1;
       const uint32_t aph = (tcount >> 1) & 1;
@@ -358,8 +357,8 @@ using namespace b200;
 // comm: optional pointer to a host-side GemmComm block (may be null).
 struct GemmComm {
   const uint32_t* a_ready;
-  const uint32_t* a_epoch_ptr;
-  int rows_per_flag;
+  const uint32_t* a_expected;
+  int m_rot;
   int rs_world, rs_rank, rows_per_rank;
   uint32_t rs_inc;
   void* peer_out[kMaxPeers];
@@ -395,8 +394,8 @@ GLLM_EXPORT int gllm_gemm_bf16(const void* A, int64_t lda, const void* W, int64_
   }
   if (comm != nullptr) {
     p.a_ready = comm->a_ready;
-    p.a_epoch_ptr = comm->a_epoch_ptr;
-    p.rows_per_flag = comm->rows_per_flag;
+    p.a_expected = comm->a_expected;
+    p.m_rot = comm->m_rot;
     p.rs_world = comm->rs_world;
     p.rs_rank = comm->rs_rank;
     p.rows_per_rank = comm->rows_per_rank;

@@ -30,8 +30,8 @@ class GemmComm(ctypes.Structure):
 
     _fields_ = [
         ("a_ready", c_void_p),
-        ("a_epoch_ptr", c_void_p),
-        ("rows_per_flag", c_int),
+        ("a_expected", c_void_p),
+        ("m_rot", c_int),
         ("rs_world", c_int),
         ("rs_rank", c_int),
         ("rows_per_rank", c_int),

@@ -37,8 +37,12 @@ class ReduceNormArgs(ctypes.Structure):
         ("local_ld", c_int64), ("residual", c_void_p), ("residual_in", c_int), ("norm_w", c_void_p),
         ("ag_peers", c_void_p * MAX_PEERS), ("flag_peers", c_void_p * MAX_PEERS), ("unnormed_out", c_void_p),
         ("st", c_void_p), ("parity", c_int), ("ag_idx", c_int), ("tp", c_int), ("rank", c_int),
-        ("rows_per_rank", c_int), ("rows_valid", c_int), ("H", c_int), ("eps", c_float),
+        ("rows_per_rank", c_int), ("rows_valid", c_int), ("H", c_int), ("eps", c_float), ("T", c_int),
     ]
+
+
+MAX_BLOCKS = 256   # kMaxBlocks in csrc/comm/tp_fused.cu (128-row blocks per gather buffer)
+SMALL_T = 64       # forwards with <= this many tokens use the NCCL strategy (see begin_forward)
 
 
 def _declare(L):
@@ -77,8 +81,9 @@ class FusedTPComm(TPComm):
         self.off_ag = [2 * stage_bytes + i * ag_bytes for i in range(3)]
         base_sync = 2 * stage_bytes + 3 * ag_bytes
         self.off_cnt = [base_sync, base_sync + 64]
-        self.off_flag = [base_sync + 128 + 64 * i for i in range(3)]
-        total = base_sync + 128 + 64 * 3
+        self.off_flag = [base_sync + 128 + 4 * MAX_BLOCKS * i for i in range(3)]
+        total = base_sync + 128 + 4 * MAX_BLOCKS * 3
+        assert t_pad <= 128 * MAX_BLOCKS
         total = (total + 255) // 256 * 256
         self.blob = symm.empty(total, dtype=torch.uint8, device=self.device)
         self.blob.zero_()
@@ -89,8 +94,9 @@ class FusedTPComm(TPComm):
         assert self.local_base == self.blob.data_ptr()
         n_state = L.gllm_tp_state_bytes()
         self.state = torch.zeros(n_state, dtype=torch.uint8, device=self.device)
-        # TpState layout: rs_expected[2][8] u32 | ag_epoch[3] u32 | ticket[4] u32
-        self.ag_epoch_ptr = [self.state.data_ptr() + 64 + 4 * i for i in range(3)]
+        # TpState layout: rs_expected[2][8] | ag_epoch[3] | ticket[4] | pad[9] | ag_expected[3][MAX_BLOCKS] (u32)
+        assert n_state == 128 + 3 * MAX_BLOCKS * 4, n_state
+        self.ag_expected_ptr = [self.state.data_ptr() + 128 + 4 * MAX_BLOCKS * i for i in range(3)]
         # device tables of peer pointers for the row-push kernel
         self.stage_tbl = [torch.tensor([b + self.off_stage[p] for b in self.peer_base], dtype=torch.int64,
                                        device=self.device) for p in range(2)]
@@ -103,12 +109,17 @@ class FusedTPComm(TPComm):
         self.rpr = 0
         self.rs_call = 0
         self.ag_call = 0
+        self.small = False
         self.cur_ag = None  # (ag_idx, tensor view) produced by the last reduce_norm
         logger.info("fused TP: %d MB symmetric buffer per rank, peers mapped over NVLink", total >> 20)
 
     # -------------------------------------------------------------------------------------------
     def begin_forward(self, num_tokens: int):
         assert num_tokens <= self.max_tokens
+        # Tiny decode batches are latency bound: the swap-AB weight-streaming GEMMs + one NCCL
+        # all-reduce beat the sharded dataflow there (measured on 2xB200: 4.6 ms vs 7.0 ms per step at
+        # batch 16), so such forwards run the baseline strategy; everything else runs fused.
+        self.small = num_tokens <= SMALL_T
         self.T = num_tokens
         self.rpr = (num_tokens + self.tp_size - 1) // self.tp_size
         self.rs_call = 0
@@ -146,6 +157,7 @@ class FusedTPComm(TPComm):
         a.st = self.state.data_ptr()
         a.parity, a.ag_idx, a.tp, a.rank = parity, ag_idx, self.tp_size, self.tp_rank
         a.rows_per_rank, a.rows_valid, a.H, a.eps = self.rpr, self._rows_valid(), self.H, float(eps)
+        a.T = self.T
         check(self.L.gllm_rs_reduce_norm(ctypes.byref(a), stream_ptr()), "rs_reduce_norm")
         from gllm_b200.ops import sm100
         sm100._count()
@@ -160,42 +172,47 @@ class FusedTPComm(TPComm):
         idx = self.cur_ag[0]
         c = GemmComm()
         c.a_ready = self.local_base + self.off_flag[idx]
-        c.a_epoch_ptr = self.ag_epoch_ptr[idx]
-        c.rows_per_flag = self.rpr
+        c.a_expected = self.ag_expected_ptr[idx]
+        num_m = (self.T + 127) // 128
+        c.m_rot = ((self.tp_rank * self.rpr) // 128) % max(num_m, 1)  # start with this rank's own rows
         c.rs_world = 0
         return c
 
     # -------------------------------------------------------------------------------------------
     def first_norm(self, x: torch.Tensor, norm_w: torch.Tensor, eps: float):
         """Embedding output (replicated) -> (normed gather buffer, residual shard)."""
+        if self.small:
+            return super().first_norm(x, norm_w, eps)
         return self._reduce_norm(0, 0, x, False, norm_w, eps)
 
     def materialize(self, h: torch.Tensor) -> torch.Tensor:
         """Make the gather buffer safe to read by a kernel that does not understand the flags."""
-        if self.cur_ag is not None and h.data_ptr() == self.cur_ag[1].data_ptr():
+        if not self.small and self.cur_ag is not None and h.data_ptr() == self.cur_ag[1].data_ptr():
             idx = self.cur_ag[0]
             check(self.L.gllm_wait_ag_flags(self.local_base + self.off_flag[idx], self.state.data_ptr(), idx,
-                                            self.tp_size, stream_ptr()), "wait_ag_flags")
+                                            self.T, stream_ptr()), "wait_ag_flags")
             from gllm_b200.ops import sm100
             sm100._count()
         return h
 
     def col_linear(self, x, w, bias=None):
         from gllm_b200.ops import sm100
-        comm = self._ag_comm(x)
+        comm = None if self.small else self._ag_comm(x)
         if comm is None:
             return sm100.linear(x, w, bias)
         return sm100.linear(x, w, bias, comm=comm)
 
     def col_linear_silu_mul(self, x, w_interleaved):
         from gllm_b200.ops import sm100
-        comm = self._ag_comm(x)
+        comm = None if self.small else self._ag_comm(x)
         if comm is None:
             return sm100.linear_silu_mul(x, w_interleaved)
         return sm100.linear_silu_mul(x, w_interleaved, comm=comm)
 
     def row_linear_add_norm(self, x, w, residual, norm_w, eps, bias=None):
         from gllm_b200.ops import sm100
+        if self.small:
+            return super().row_linear_add_norm(x, w, residual, norm_w, eps, bias)
         parity = self.rs_call % 2
         self.rs_call += 1
         t, n = x.shape[0], w.shape[0]
@@ -215,6 +232,8 @@ class FusedTPComm(TPComm):
 
     def reduce_add_norm(self, partial, residual, norm_w, eps):
         from gllm_b200.ops import sm100
+        if self.small:
+            return super().reduce_add_norm(partial, residual, norm_w, eps)
         parity = self.rs_call % 2
         self.rs_call += 1
         assert partial.shape[0] == self.T and partial.shape[1] == self.H and partial.stride(1) == 1
@@ -225,6 +244,8 @@ class FusedTPComm(TPComm):
         return self._reduce_norm(parity, self._rows_valid(), None, residual is not None, norm_w, eps)
 
     def row_linear(self, x, w, bias=None):
+        if self.small:
+            return super().row_linear(x, w, bias)
         raise NotImplementedError("fused TP is used with pp_size == 1 (no un-normalised stage boundary)")
 
 

@@ -309,3 +309,37 @@ def mark_seen(seen_bits: torch.Tensor, rows: torch.Tensor, tokens: torch.Tensor)
     check(L.gllm_mark_seen(_p(seen_bits), seen_bits.shape[1], _p(rows), _p(tokens), rows.numel(), stream_ptr()),
           "mark_seen")
     _count()
+
+
+# ----------------------------------------------------------------------------------------------
+# fp8 block-scaled GEMM (DeepSeek-V3 / Qwen3-FP8 checkpoints)
+# ----------------------------------------------------------------------------------------------
+def fp8_quant_group(x: torch.Tensor):
+    """bf16 [M, K] -> (e4m3 [M, K], fp32 scales [K/128, M]) — dynamic per-token-group(128) quantisation."""
+    assert x.dtype == _BF16 and x.dim() == 2 and x.stride(1) == 1 and x.shape[1] % 128 == 0
+    m, k = x.shape
+    q = torch.empty(m, k, dtype=torch.float8_e4m3fn, device=x.device)
+    s = torch.empty(k // 128, m, dtype=torch.float32, device=x.device)
+    L = _lib.load()
+    check(L.gllm_fp8_quant_group(_p(x), x.stride(0), _p(q), _p(s), m, k, stream_ptr()), "fp8_quant_group")
+    _count()
+    return q, s
+
+
+def linear_fp8_block(x: torch.Tensor, w8: torch.Tensor, w_scale_inv: torch.Tensor,
+                     bias: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """x bf16 [M,K]; w8 e4m3 [N,K]; w_scale_inv fp32 [ceil(N/128), K/128] -> bf16 [M,N]."""
+    assert w8.dtype == torch.float8_e4m3fn and w8.is_contiguous() and w_scale_inv.dtype == torch.float32
+    assert w_scale_inv.is_contiguous()
+    m, k = x.shape
+    n = w8.shape[0]
+    if out is None:
+        out = torch.empty(m, n, dtype=_BF16, device=x.device)
+    if m == 0:
+        return out
+    xq, xs = fp8_quant_group(x)
+    L = _lib.load()
+    check(L.gllm_gemm_fp8_block(_p(xq), _p(xs), _p(w8), _p(w_scale_inv), _p(out), out.stride(0), m, n, k, _p(bias),
+                                stream_ptr()), "gemm_fp8_block")
+    _count()
+    return out

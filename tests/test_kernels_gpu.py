@@ -346,3 +346,27 @@ def test_moe_fused_experts(t, e, k, h, i, ep):
     y_ref = ref.fused_experts(x, w13, w2, w, ids, emap)
     assert torch.isfinite(y.float()).all()
     assert _rel_err(y, y_ref) < 2e-2, _rel_err(y, y_ref)
+
+
+@pytest.mark.parametrize("m,n,k", [(1, 256, 128), (77, 1536, 512), (300, 4096, 7168), (1024, 2048, 2048)])
+def test_gemm_fp8_block(m, n, k):
+    from gllm_b200.ops import sm100
+    torch.manual_seed(m)
+    x = (torch.randn(m, k, device=_dev()) * 0.7).bfloat16()
+    w = torch.randn(n, k, device=_dev()) * 0.05
+    # block-quantise the weight like an HF fp8 checkpoint: per 128x128 block scale_inv = amax / 448
+    nb, kb = (n + 127) // 128, k // 128
+    wp = torch.zeros(nb * 128, k, device=_dev())
+    wp[:n] = w
+    blocks = wp.view(nb, 128, kb, 128)
+    s_inv = (blocks.abs().amax(dim=(1, 3)) / 448.0).clamp_min(1e-8)
+    w8 = (blocks / s_inv.view(nb, 1, kb, 1)).view(nb * 128, k)[:n].to(torch.float8_e4m3fn).contiguous()
+    b = torch.randn(n, device=_dev()).bfloat16()
+    y = sm100.linear_fp8_block(x, w8, s_inv.contiguous(), b)
+    y_ref = ref.linear_fp8_block(x, w8, s_inv, b)
+    assert _rel_err(y, y_ref) < 1e-2, _rel_err(y, y_ref)
+    # and the quantiser alone
+    q, s = sm100.fp8_quant_group(x)
+    q_r, s_r = ref.fp8_quant_group(x)
+    assert torch.allclose(s.t(), s_r, rtol=1e-5)
+    assert _rel_err(q.float(), q_r.float()) < 3e-2

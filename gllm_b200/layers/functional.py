@@ -18,6 +18,10 @@ def _sm():
 
 
 def linear(x, w, bias=None, out=None):
+    if isinstance(w, tuple):  # (e4m3 weight, fp32 block scale_inv): block-scaled fp8 GEMM
+        if x.is_cuda:
+            return _sm().linear_fp8_block(x, w[0], w[1], bias, out=out)
+        return ref.linear_fp8_block(x, w[0], w[1], bias)
     if x.is_cuda:
         return _sm().linear(x, w, bias, out=out)
     return ref.linear(x, w, bias)

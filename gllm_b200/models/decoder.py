@@ -72,6 +72,7 @@ class ModelSpec:
     names: Dict[str, str] = field(default_factory=dict)
     eos_token_id: Optional[object] = None
     extra: dict = field(default_factory=dict)
+    quant: Optional[str] = None  # "fp8": block-scaled e4m3 linears (HF quantization_config, 128x128 blocks)
 
     def is_moe_layer(self, layer_id: int) -> bool:
         if self.moe is None:
@@ -103,6 +104,40 @@ def _param(*shape, dtype, device, std=0.02, fill=None):
     return nn.Parameter(t, requires_grad=False)
 
 
+def _linear_params(n: int, k: int, spec: ModelSpec, device):
+    """(weight, scale_inv | None): bf16 [n, k], or e4m3 [n, k] + fp32 block scales for fp8 checkpoints."""
+    if spec.quant == "fp8":
+        w = nn.Parameter(torch.zeros(n, k, dtype=torch.float8_e4m3fn, device=device), requires_grad=False)
+        s = nn.Parameter(torch.ones((n + 127) // 128, (k + 127) // 128, dtype=torch.float32, device=device),
+                         requires_grad=False)
+        return w, s
+    return _param(n, k, dtype=spec.dtype, device=device), None
+
+
+def _qw(w, s):
+    """Weight handle passed to the linear ops: plain tensor, or (e4m3, scale_inv) for fp8."""
+    return w if s is None else (w, s)
+
+
+def _store_linear(w_param, s_param, w: torch.Tensor):
+    """Copy a (sharded) weight into its parameter; fp8 parameters are block-quantised here (128x128 blocks,
+    scale_inv = amax / 448). Re-quantising the de-quantised tensor of an fp8 checkpoint is lossless as long
+    as shard boundaries fall on block boundaries (they do: head_dim 128, intermediate % 128 == 0)."""
+    if s_param is None:
+        w_param.data.copy_(w)
+        return
+    w = w.float()
+    n, k = w.shape
+    nb, kb = (n + 127) // 128, (k + 127) // 128
+    wp = torch.zeros(nb * 128, kb * 128, dtype=torch.float32, device=w.device)
+    wp[:n, :k] = w
+    blk = wp.view(nb, 128, kb, 128)
+    sc = (blk.abs().amax(dim=(1, 3)) / 448.0).clamp_min(1e-12)
+    q = (blk / sc.view(nb, 1, kb, 1)).view(nb * 128, kb * 128)[:n, :k].to(torch.float8_e4m3fn)
+    w_param.data.copy_(q)
+    s_param.data.copy_(sc)
+
+
 class Attention(nn.Module):
     def __init__(self, spec: ModelSpec, layer_id: int, rope: RopeSpec, device):
         super().__init__()
@@ -119,16 +154,16 @@ class Attention(nn.Module):
         self.rope = rope
         self.eps = spec.rms_eps
         h, dt = spec.hidden_size, spec.dtype
-        self.qkv_w = _param(self.q_size + 2 * self.kv_size, h, dtype=dt, device=device)
+        self.qkv_w, self.qkv_ws = _linear_params(self.q_size + 2 * self.kv_size, h, spec, device)
         self.qkv_b = _param(self.q_size + 2 * self.kv_size, dtype=dt, device=device) if spec.qkv_bias else None
-        self.o_w = _param(h, self.q_size, dtype=dt, device=device)
+        self.o_w, self.o_ws = _linear_params(h, self.q_size, spec, device)
         self.o_b = _param(h, dtype=dt, device=device) if spec.o_bias else None
         self.q_norm_w = _param(self.head_dim, dtype=dt, device=device, fill=1.0) if spec.qk_norm else None
         self.k_norm_w = _param(self.head_dim, dtype=dt, device=device, fill=1.0) if spec.qk_norm else None
 
     def forward(self, inp, h: torch.Tensor, kv_cache, tpc: TPComm) -> torch.Tensor:
         """h [T, H] (normed) -> attention output [T, q_size] (input of the row-parallel O-proj)."""
-        qkv = tpc.col_linear(h, self.qkv_w, self.qkv_b)
+        qkv = tpc.col_linear(h, _qw(self.qkv_w, self.qkv_ws), self.qkv_b)
         t = qkv.shape[0]
         d = self.head_dim
         q = qkv[:, : self.q_size].view(t, self.num_heads, d)
@@ -145,26 +180,35 @@ class Attention(nn.Module):
 
 
 class DenseMLP(nn.Module):
-    def __init__(self, hidden: int, intermediate: int, dtype, device, shard: bool = True):
+    def __init__(self, hidden: int, intermediate: int, dtype, device, shard: bool = True,
+                 spec: Optional[ModelSpec] = None):
         super().__init__()
         tp = ps.get_tp_size() if shard else 1
         assert intermediate % tp == 0
         self.inter = intermediate // tp
-        # fused SiLU-gate epilogue needs the gate/up rows interleaved per 128
-        self.fused_act = self.inter % 128 == 0
-        self.gate_up_w = _param(2 * self.inter, hidden, dtype=dtype, device=device)
-        self.down_w = _param(hidden, self.inter, dtype=dtype, device=device)
+        fp8 = spec is not None and spec.quant == "fp8"
+        # fused SiLU-gate epilogue needs the gate/up rows interleaved per 128 (bf16 kernel only)
+        self.fused_act = self.inter % 128 == 0 and not fp8
+        if fp8:
+            self.gate_up_w, self.gate_up_ws = _linear_params(2 * self.inter, hidden, spec, device)
+            self.down_w, self.down_ws = _linear_params(hidden, self.inter, spec, device)
+        else:
+            self.gate_up_w, self.gate_up_ws = _param(2 * self.inter, hidden, dtype=dtype, device=device), None
+            self.down_w, self.down_ws = _param(hidden, self.inter, dtype=dtype, device=device), None
 
     def set_gate_up(self, gate_up: torch.Tensor):
         """gate_up [2*inter, H] = [gate rows; up rows] for this rank."""
         if self.fused_act:
             gate_up = ref.interleave_gate_up(gate_up, 128)
-        self.gate_up_w.data.copy_(gate_up)
+        _store_linear(self.gate_up_w, self.gate_up_ws, gate_up)
+
+    def down_weight(self):
+        return _qw(self.down_w, self.down_ws)
 
     def act(self, h: torch.Tensor, tpc: TPComm) -> torch.Tensor:
         if self.fused_act:
             return tpc.col_linear_silu_mul(h, self.gate_up_w)
-        return Fn.silu_and_mul(tpc.col_linear(h, self.gate_up_w))
+        return Fn.silu_and_mul(tpc.col_linear(h, _qw(self.gate_up_w, self.gate_up_ws)))
 
 
 class DecoderLayer(nn.Module):
@@ -181,7 +225,7 @@ class DecoderLayer(nn.Module):
         if self.is_moe:
             self.mlp = moe_factory(spec, layer_id, device)
         else:
-            self.mlp = DenseMLP(h, spec.intermediate_size, dt, device)
+            self.mlp = DenseMLP(h, spec.intermediate_size, dt, device, spec=spec)
 
     def forward(self, inp, h: torch.Tensor, residual: torch.Tensor, kv_cache, tpc: TPComm,
                 next_norm_w: Optional[torch.Tensor]):
@@ -190,7 +234,7 @@ class DecoderLayer(nn.Module):
         when `next_norm_w` is None (last layer of a non-final pipeline stage)."""
         eps = self.spec.rms_eps
         a = self.attn(inp, h, kv_cache, tpc)
-        h, residual = tpc.row_linear_add_norm(a, self.attn.o_w, residual, self.post_norm_w, eps, self.attn.o_b)
+        h, residual = tpc.row_linear_add_norm(a, _qw(self.attn.o_w, self.attn.o_ws), residual, self.post_norm_w, eps, self.attn.o_b)
         if self.is_moe:
             partial = self.mlp(tpc.materialize(h), tpc)
             if next_norm_w is None:
@@ -198,8 +242,8 @@ class DecoderLayer(nn.Module):
             return tpc.reduce_add_norm(partial, residual, next_norm_w, eps)
         act = self.mlp.act(h, tpc)
         if next_norm_w is None:
-            return tpc.row_linear(act, self.mlp.down_w), residual
-        return tpc.row_linear_add_norm(act, self.mlp.down_w, residual, next_norm_w, eps)
+            return tpc.row_linear(act, self.mlp.down_weight()), residual
+        return tpc.row_linear_add_norm(act, self.mlp.down_weight(), residual, next_norm_w, eps)
 
 
 class CausalLM(nn.Module):
@@ -291,6 +335,14 @@ class CausalLM(nn.Module):
                 p.data.fill_(1.0)
             elif p.dim() == 1:
                 p.data.zero_()
+            elif p.dtype == torch.float8_e4m3fn:
+                step = 1 << 26
+                flat = p.data.view(-1)
+                for s0 in range(0, flat.numel(), step):
+                    e0 = min(s0 + step, flat.numel())
+                    flat[s0:e0].copy_((torch.randn(e0 - s0, device=p.device) * 100.0).to(torch.float8_e4m3fn))
+            elif name.endswith("_ws"):
+                p.data.fill_(0.02 / 100.0)
             elif p.is_cuda:
                 p.data.normal_(mean=0.0, std=0.02)  # on-device RNG: 8B params in well under a second
             else:
@@ -347,7 +399,7 @@ class CausalLM(nn.Module):
             q = reader.get(pre + nm["q"] + ".weight")
             k = reader.get(pre + nm["k"] + ".weight")
             v = reader.get(pre + nm["v"] + ".weight")
-        at.qkv_w.data.copy_(wu.shard_qkv(q, k, v, spec.num_heads, spec.num_kv_heads, d, tr, tp))
+        _store_linear(at.qkv_w, at.qkv_ws, wu.shard_qkv(q, k, v, spec.num_heads, spec.num_kv_heads, d, tr, tp))
         if at.qkv_b is not None:
             if "qkv_fused" in nm:
                 b = reader.get(pre + nm["qkv_fused"] + ".bias")
@@ -355,7 +407,7 @@ class CausalLM(nn.Module):
             else:
                 qb, kb, vb = (reader.get(pre + nm[x] + ".bias") for x in ("q", "k", "v"))
             at.qkv_b.data.copy_(wu.shard_qkv(qb, kb, vb, spec.num_heads, spec.num_kv_heads, d, tr, tp))
-        at.o_w.data.copy_(wu.shard_cols(reader.get(pre + nm["o"] + ".weight"), tr, tp))
+        _store_linear(at.o_w, at.o_ws, wu.shard_cols(reader.get(pre + nm["o"] + ".weight"), tr, tp))
         if at.o_b is not None:
             at.o_b.data.copy_(reader.get(pre + nm["o"] + ".bias"))
         if at.q_norm_w is not None:
@@ -371,4 +423,4 @@ class CausalLM(nn.Module):
             gate = reader.get(pre + nm["gate"] + ".weight")
             up = reader.get(pre + nm["up"] + ".weight")
         mlp.set_gate_up(wu.shard_gate_up(gate, up, tr, tp))
-        mlp.down_w.data.copy_(wu.shard_cols(reader.get(pre + nm["down"] + ".weight"), tr, tp))
+        _store_linear(mlp.down_w, mlp.down_ws, wu.shard_cols(reader.get(pre + nm["down"] + ".weight"), tr, tp))

@@ -56,6 +56,9 @@ def _base_spec(cfg: HFConfig, arch: str, **kw) -> ModelSpec:
         max_position=cfg.get("max_position_embeddings", 8192), rope_theta=rope_theta,
         rope_scaling=dict(rope_scaling) if rope_scaling else None, dtype=_dtype(cfg),
         eos_token_id=cfg.get("eos_token_id"))
+    qc = cfg.get("quantization_config") or {}
+    if qc.get("quant_method") == "fp8" and list(qc.get("weight_block_size") or []) == [128, 128]:
+        spec.quant = "fp8"
     for k, v in kw.items():
         setattr(spec, k, v)
     return spec

@@ -146,13 +146,36 @@ class CheckpointReader:
             self._handles[fpath] = h
         return h
 
-    def get(self, name: str) -> torch.Tensor:
+    def get_raw(self, name: str) -> torch.Tensor:
         key = self.resolve(name)
         if key is None:
             raise KeyError(f"tensor {name} not found in checkpoint {self.path}")
         if key in self._bin:
             return self._bin[key]
         return self._handle(self._files[key]).get_tensor(key)
+
+    def get(self, name: str) -> torch.Tensor:
+        """Tensor by name. Block-quantised fp8 weights (`<name>` e4m3 + `<name>_scale_inv` fp32 per
+        128x128 block — DeepSeek-V3 / Qwen3-FP8 checkpoints, reference: gllm/layers/linear.py:68-112)
+        are de-quantised to bf16 here unless the caller asks for the raw pair via `get_fp8`."""
+        t = self.get_raw(name)
+        if t.dtype in (torch.float8_e4m3fn, torch.float8_e5m2) and self.has(name + "_scale_inv"):
+            s = self.get_raw(name + "_scale_inv").float()
+            n, k = t.shape
+            bn, bk = -(-n // s.shape[0]), -(-k // s.shape[1])
+            full = s.repeat_interleave(bn, 0)[:n].repeat_interleave(bk, 1)[:, :k]
+            return (t.float() * full).to(torch.bfloat16)
+        return t
+
+    def is_fp8(self, name: str) -> bool:
+        key = self.resolve(name)
+        if key is None or not self.has(name + "_scale_inv"):
+            return False
+        return self.get_raw(name).dtype == torch.float8_e4m3fn
+
+    def get_fp8(self, name: str):
+        """(e4m3 weight, fp32 scale_inv [ceil(N/128), ceil(K/128)])"""
+        return self.get_raw(name), self.get_raw(name + "_scale_inv").float()
 
     def get_rows(self, name: str, start: int, end: int) -> torch.Tensor:
         key = self.resolve(name)

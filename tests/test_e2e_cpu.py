@@ -180,3 +180,28 @@ def test_deepseek_v3_mla_moe_matches_hf():
         if "e_score_correction_bias" in n:
             b.normal_(std=0.05)
     _check(m)
+
+
+def test_fp8_block_quantised_model_close_to_hf():
+    """`quantization_config: fp8 / weight_block_size [128,128]` -> linears run the block-scaled fp8 path
+    (activations quantised per token per 128 group). Quantisation noise may flip late tokens; the first
+    tokens must agree with the unquantised HF model."""
+    import json
+    from transformers import Qwen3Config, Qwen3ForCausalLM
+    torch.manual_seed(11)
+    cfg = Qwen3Config(hidden_size=256, intermediate_size=512, num_hidden_layers=2, num_attention_heads=4,
+                      num_key_value_heads=2, head_dim=64, vocab_size=512, max_position_embeddings=512,
+                      eos_token_id=1, tie_word_embeddings=False)
+    m = Qwen3ForCausalLM(cfg).eval().float()
+    d = _save(m)
+    c = json.load(open(os.path.join(d, "config.json")))
+    c["quantization_config"] = {"quant_method": "fp8", "activation_scheme": "dynamic", "fmt": "e4m3",
+                                "weight_block_size": [128, 128]}
+    json.dump(c, open(os.path.join(d, "config.json"), "w"))
+    llm = _engine(d)
+    model = llm.worker.runner.model
+    assert model.spec.quant == "fp8" and model.layers[0].attn.qkv_w.dtype == torch.float8_e4m3fn
+    outs = llm.generate(tokens=PROMPTS, output_lens=[4] * len(PROMPTS), ignore_eos=True)
+    same_first = sum(s.token_ids[len(p)] == _hf_greedy(m, p, 1)[0] for p, s in zip(PROMPTS, outs))
+    assert same_first >= len(PROMPTS) - 1
+    llm.shutdown()

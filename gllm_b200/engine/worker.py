@@ -200,8 +200,11 @@ class Worker(ProfilerMixin):
         if not ps.is_first_pp_rank():
             t = batch.num_tokens
             hidden, residual = self.runner.input_hidden[:t], self.runner.input_residual[:t]
-            ps.pp_recv([hidden, residual] if self.runner.model.ret_residual else [hidden])
-        res = self.runner.step(batch, hidden, residual)
+            # tile-streamed receive: all irecvs are posted now, the compute stream waits per tile
+            tiles = ps.pp_recv_tiled([hidden, residual] if self.runner.model.ret_residual else [hidden])
+        else:
+            tiles = None
+        res = self.runner.step(batch, hidden, residual, recv_tiles=tiles)
         if ps.is_last_pp_rank():
             if ps.is_output_rank():
                 self.comm.send_tokens(batch.batch_id, res.tokens_list())
@@ -214,7 +217,7 @@ class Worker(ProfilerMixin):
         # clone: the static output buffers are overwritten by the next micro-batch while the send is
         # still in flight (latent race in the reference)
         tensors = [t.clone() for t in tensors]
-        handles = ps.pp_send(tensors)
+        handles = ps.pp_send_tiled(tensors)
         self.inflight_sends.append((handles, tensors))
 
     def _reap_sends(self):

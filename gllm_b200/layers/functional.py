@@ -33,11 +33,18 @@ def linear_silu_mul(x, w_interleaved):
     return ref.linear_silu_mul(x, w_interleaved)
 
 
-def rmsnorm(x, w, eps, residual=None):
+def rmsnorm(x, w, eps, residual=None, out=None):
     """-> (normed, residual_out). With `residual`, computes residual += x first (in place on GPU)."""
     if x.is_cuda:
-        return _sm().rmsnorm(x, w, eps, residual)
-    return ref.rmsnorm(x, w, eps, residual)
+        return _sm().rmsnorm(x, w, eps, residual, out=out)
+    o, r = ref.rmsnorm(x, w, eps, residual)
+    if out is not None:
+        out.copy_(o)
+        o = out
+    if residual is not None:
+        residual.copy_(r)  # same in-place contract as the GPU kernel
+        r = residual
+    return o, r
 
 
 def silu_and_mul(x):

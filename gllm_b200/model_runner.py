@@ -161,11 +161,14 @@ class ModelRunner:
         inp.load(batch)
         return self._forward_loaded(hidden, residual, use_kv)
 
-    def _forward_loaded(self, hidden, residual, use_kv=True, all_rows=False):
+    def _forward_loaded(self, hidden, residual, use_kv=True, all_rows=False, recv_tiles=None):
         inp = self.input_data
         kv = self.kv_cache if use_kv else None
         self.tpc.begin_forward(inp.padded_tokens or inp.num_tokens)
-        h, r = self.model(inp, kv, self.tpc, hidden, residual)
+        if recv_tiles is not None:
+            h, r = self.model(inp, kv, self.tpc, hidden, residual, recv_tiles=recv_tiles)
+        else:
+            h, r = self.model(inp, kv, self.tpc, hidden, residual)
         if ps.is_last_pp_rank():
             return self.model.compute_logits(inp, h, self.tpc, all_rows=all_rows), None
         return h, r
@@ -219,7 +222,7 @@ class ModelRunner:
 
     # -------------------------------------------------------------------------------------------
     def step(self, batch: BatchArrays, hidden: Optional[torch.Tensor] = None,
-             residual: Optional[torch.Tensor] = None) -> StepResult:
+             residual: Optional[torch.Tensor] = None, recv_tiles=None) -> StepResult:
         inp = self.input_data
         self.stats["steps"] += 1
         self.stats["tokens"] += batch.num_tokens
@@ -232,7 +235,7 @@ class ModelRunner:
             ev0 = torch.cuda.Event(enable_timing=True)
             ev0.record()
         try:
-            return self._step_loaded(batch, bucket, hidden, residual)
+            return self._step_loaded(batch, bucket, hidden, residual, recv_tiles)
         finally:
             if self.time_steps and self.device.type == "cuda":
                 ev1 = torch.cuda.Event(enable_timing=True)
@@ -247,8 +250,13 @@ class ModelRunner:
         self._step_events = []
         return tot
 
-    def _step_loaded(self, batch, bucket, hidden, residual) -> StepResult:
+    def _step_loaded(self, batch, bucket, hidden, residual, recv_tiles=None) -> StepResult:
         inp = self.input_data
+        if bucket is not None and recv_tiles:
+            for _, _, works in recv_tiles:  # graphs read the static input buffers: need every tile
+                for w in works:
+                    w.wait()
+            recv_tiles = None
         if bucket is not None:
             g, splits = self.graphs[bucket]
             inp.pad_for_graph(bucket, (self.num_pages - 1) * self.page_size, self.num_pages - 1)
@@ -261,7 +269,7 @@ class ModelRunner:
                 return self._sample(batch, logits)
             h, r = self.graph_hidden[bucket]
             return StepResult(hidden=h[: batch.num_tokens], residual=r[: batch.num_tokens])
-        out, r = self._forward_loaded(hidden, residual)
+        out, r = self._forward_loaded(hidden, residual, recv_tiles=recv_tiles)
         if ps.is_last_pp_rank():
             return self._sample(batch, out)
         return StepResult(hidden=out, residual=r)

@@ -161,9 +161,14 @@ class Attention(nn.Module):
         self.q_norm_w = _param(self.head_dim, dtype=dt, device=device, fill=1.0) if spec.qk_norm else None
         self.k_norm_w = _param(self.head_dim, dtype=dt, device=device, fill=1.0) if spec.qk_norm else None
 
-    def forward(self, inp, h: torch.Tensor, kv_cache, tpc: TPComm) -> torch.Tensor:
-        """h [T, H] (normed) -> attention output [T, q_size] (input of the row-parallel O-proj)."""
-        qkv = tpc.col_linear(h, _qw(self.qkv_w, self.qkv_ws), self.qkv_b)
+    def qkv_proj(self, h: torch.Tensor, tpc: TPComm) -> torch.Tensor:
+        return tpc.col_linear(h, _qw(self.qkv_w, self.qkv_ws), self.qkv_b)
+
+    def forward(self, inp, h: torch.Tensor, kv_cache, tpc: TPComm, qkv: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """h [T, H] (normed) -> attention output [T, q_size] (input of the row-parallel O-proj).
+        `qkv` may be supplied pre-computed (tile-streamed pipeline input)."""
+        if qkv is None:
+            qkv = self.qkv_proj(h, tpc)
         t = qkv.shape[0]
         d = self.head_dim
         q = qkv[:, : self.q_size].view(t, self.num_heads, d)
@@ -228,12 +233,12 @@ class DecoderLayer(nn.Module):
             self.mlp = DenseMLP(h, spec.intermediate_size, dt, device, spec=spec)
 
     def forward(self, inp, h: torch.Tensor, residual: torch.Tensor, kv_cache, tpc: TPComm,
-                next_norm_w: Optional[torch.Tensor]):
+                next_norm_w: Optional[torch.Tensor], qkv: Optional[torch.Tensor] = None):
         """h = RMSNorm'ed block input, residual = running residual stream.
         Returns (normed input of the next block, residual) — or (un-normed block output, residual)
         when `next_norm_w` is None (last layer of a non-final pipeline stage)."""
         eps = self.spec.rms_eps
-        a = self.attn(inp, h, kv_cache, tpc)
+        a = self.attn(inp, h, kv_cache, tpc, qkv=qkv)
         h, residual = tpc.row_linear_add_norm(a, _qw(self.attn.o_w, self.attn.o_ws), residual, self.post_norm_w, eps, self.attn.o_b)
         if self.is_moe:
             partial = self.mlp(tpc.materialize(h), tpc)
@@ -297,7 +302,8 @@ class CausalLM(nn.Module):
         return tpc.all_reduce(x)
 
     def forward(self, inp, kv_cache, tpc: TPComm, hidden: Optional[torch.Tensor] = None,
-                residual: Optional[torch.Tensor] = None, inputs_embeds: Optional[torch.Tensor] = None):
+                residual: Optional[torch.Tensor] = None, inputs_embeds: Optional[torch.Tensor] = None,
+                recv_tiles=None):
         """First stage: tokens -> ... ; later stages: (hidden, residual) from the previous stage.
         Returns (hidden, residual): on the last stage `hidden` is the final-normed activation."""
         eps = self.spec.rms_eps
@@ -307,16 +313,43 @@ class CausalLM(nn.Module):
             if n == 0:
                 return x, None
             h, residual = tpc.first_norm(x, self.layers[0].input_norm_w, eps)
-        else:
+        qkv0 = None
+        else_branch = not self.is_first
+        if else_branch:
             if n == 0:
+                if recv_tiles:
+                    for _, _, works in recv_tiles:
+                        for w in works:
+                            w.wait()
                 return hidden, residual
-            h, residual = Fn.rmsnorm(hidden, self.layers[0].input_norm_w, eps, residual)
+            if recv_tiles and len(recv_tiles) > 1 and hasattr(self.layers[0].attn, "qkv_proj"):
+                # tile-streamed pipeline input: add+RMSNorm and the QKV GEMM run per row tile as the tiles
+                # land, overlapping the NCCL transfer of the following tiles
+                h = torch.empty_like(hidden)
+                at = self.layers[0].attn
+                for r0, r1, works in recv_tiles:
+                    for w in works:
+                        w.wait()  # stream-level wait on this tile only
+                    Fn.rmsnorm(hidden[r0:r1], self.layers[0].input_norm_w, eps, residual[r0:r1], out=h[r0:r1])
+                    q = at.qkv_proj(h[r0:r1], tpc)
+                    if qkv0 is None:
+                        qkv0 = torch.empty(hidden.shape[0], q.shape[1], dtype=q.dtype, device=q.device)
+                    qkv0[r0:r1].copy_(q)
+            else:
+                if recv_tiles:
+                    for _, _, works in recv_tiles:
+                        for w in works:
+                            w.wait()
+                h, residual = Fn.rmsnorm(hidden, self.layers[0].input_norm_w, eps, residual)
         for i, layer in enumerate(self.layers):
             if i + 1 < n:
                 nxt = self.layers[i + 1].input_norm_w
             else:
                 nxt = self.final_norm_w if self.is_last else None
-            h, residual = layer(inp, h, residual, kv_cache, tpc, nxt)
+            if i == 0 and qkv0 is not None:
+                h, residual = layer(inp, h, residual, kv_cache, tpc, nxt, qkv=qkv0)
+            else:
+                h, residual = layer(inp, h, residual, kv_cache, tpc, nxt)
         return h, residual
 
     def compute_logits(self, inp, hidden: torch.Tensor, tpc: TPComm, all_rows: bool = False) -> torch.Tensor:

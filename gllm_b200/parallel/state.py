@@ -213,3 +213,36 @@ def pp_recv(tensors: List[torch.Tensor], src: Optional[int] = None):
 def divide(a: int, b: int) -> int:
     assert a % b == 0, f"{a} is not divisible by {b}"
     return a // b
+
+
+# ------------------------------------------------------------------------------------------------
+# tile-streamed PP p2p: the activation travels as row tiles over NCCL p2p; the receiver
+# posts every tile's irecv up front and lets its compute stream wait per tile, so the first layer's
+# add+RMSNorm and QKV GEMM of tile i overlap the transfer of tiles i+1.. (the reference blocks on the
+# whole tensor, gllm/worker.py:141-157).
+# ------------------------------------------------------------------------------------------------
+def pp_row_tiles(num_rows: int, min_rows: Optional[int] = None, max_tiles: int = 8):
+    if min_rows is None:
+        import os
+        min_rows = int(os.environ.get("GLLM_PP_TILE_ROWS", "512"))
+    n = max(1, min(max_tiles, num_rows // min_rows))
+    per = (num_rows + n - 1) // n
+    return [(i * per, min((i + 1) * per, num_rows)) for i in range(n) if i * per < num_rows]
+
+
+def pp_send_tiled(tensors: List[torch.Tensor], dst: Optional[int] = None):
+    dst = get_next_pp_rank() if dst is None else dst
+    handles = []
+    for r0, r1 in pp_row_tiles(tensors[0].shape[0]):
+        for t in tensors:
+            handles.append(dist.isend(t[r0:r1], dst))
+    return handles
+
+
+def pp_recv_tiled(tensors: List[torch.Tensor], src: Optional[int] = None):
+    """-> [(r0, r1, [work per tensor])]; call `w.wait()` (stream-level) before touching rows r0:r1."""
+    src = get_prev_pp_rank() if src is None else src
+    out = []
+    for r0, r1 in pp_row_tiles(tensors[0].shape[0]):
+        out.append((r0, r1, [dist.irecv(t[r0:r1], src) for t in tensors]))
+    return out

@@ -47,3 +47,10 @@ def test_pp2_tp2_token_throttling_matches_single(single):
 def test_mixtral_ep2_matches_single():
     ref = _run(1, 1, arch="MixtralForCausalLM")
     assert _run(1, 2, arch="MixtralForCausalLM", port=29851) == ref
+
+
+def test_pp2_tile_streamed_recv_matches_single(single, monkeypatch):
+    """Force tiny row tiles so the stage-1 input really arrives as several NCCL/gloo p2p tiles and the
+    first layer's add+norm / QKV projection run per tile."""
+    monkeypatch.setenv("GLLM_PP_TILE_ROWS", "8")
+    assert _run(2, 1, port=29871) == single

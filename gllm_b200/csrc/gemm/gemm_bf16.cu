@@ -49,6 +49,9 @@ struct GemmParams {
   const int32_t* tile_expert;
   const int32_t* num_m_tiles_ptr;  // device scalar: number of live M tiles
   int n_per_expert;
+  // per-row destination table (EP combine push): row r of C is stored at row_dest[r] (any rank's memory
+  // mapped over NVLink); 0 = padding row, not stored. comm/ep_a2a.cu builds the table.
+  const int64_t* row_dest;
 };
 
 template <int BN>
@@ -194,14 +197,18 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       mbar_wait(&tmem_full[buf], aph);
       tc_fence_after();
       const int row = m0 + q * 32 + lane;
-      const bool row_ok = row < p.M;
+      const bool row_in = row < p.M;
       const uint32_t t_row = tmem_base + buf * BN + (static_cast<uint32_t>(q * 32) << 16);
 
       // destination row pointer (local C, or the owner rank's staging buffer for RS)
       __nv_bfloat16* crow = nullptr;
       int out_n0 = (EPI == kEpiSiluMul) ? n0 / 2 : n0;
       const int out_N = (EPI == kEpiSiluMul) ? p.N / 2 : p.N;
-      if (row_ok) {
+      bool row_ok = row_in;
+      if (row_in && p.row_dest != nullptr) {
+        crow = reinterpret_cast<__nv_bfloat16*>(p.row_dest[row]);
+        row_ok = crow != nullptr;
+      } else if (row_ok) {
         if (p.rs_world > 0) {
           const int owner = row / p.rows_per_rank;
           const int r_local = row - owner * p.rows_per_rank;
@@ -440,7 +447,7 @@ GLLM_EXPORT int gllm_gemm_bf16_tiles_covering(int M, int N, int epi, int force_b
 // epi: 0 store, 1 SiLU-gate (slab rows interleaved per 64 like the dense gate/up weight).
 GLLM_EXPORT int gllm_moe_grouped_gemm(const void* A, int64_t lda, const void* W, void* C, int64_t ldc,
                                       int max_tiles, int N, int K, int E, const void* tile_expert,
-                                      const void* num_tiles_ptr, int epi, void* stream) {
+                                      const void* num_tiles_ptr, int epi, const void* row_dest, void* stream) {
   if (max_tiles <= 0) return 0;
   if ((K % 8) != 0 || (N % 8) != 0 || (lda % 8) != 0 || (ldc % 8) != 0) return 1;
   const int bn = 128;  // 64|64 gate/up interleave for the SiLU epilogue; good balance for expert tiles
@@ -457,6 +464,7 @@ GLLM_EXPORT int gllm_moe_grouped_gemm(const void* A, int64_t lda, const void* W,
   p.tile_expert = reinterpret_cast<const int32_t*>(tile_expert);
   p.num_m_tiles_ptr = reinterpret_cast<const int32_t*>(num_tiles_ptr);
   p.n_per_expert = N;
+  p.row_dest = reinterpret_cast<const int64_t*>(row_dest);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   return epi == kEpiSiluMul ? launch_gemm<128, kEpiSiluMul>(ta, tb, p, st) : launch_gemm<128, kEpiStore>(ta, tb, p, st);
 }

@@ -170,10 +170,11 @@ __global__ void grouped_topk_kernel(const __nv_bfloat16* __restrict__ logits, in
 // meta layout (int32): [0] num_tiles, [1] num_rows_padded, [2..2+E) counts, [2+E .. 2+2E) cursors,
 //                      [2+2E .. 2+3E+1) padded offsets
 // ---------------------------------------------------------------------------------------------
+// n_valid (optional device scalar): only the first *n_valid slots are live (EP receive pool, comm/ep_a2a.cu)
 __global__ void moe_count_kernel(const int32_t* __restrict__ ids, const int32_t* __restrict__ expert_map, int n_slots,
-                                 int E_local, int32_t* __restrict__ meta) {
+                                 int E_local, int32_t* __restrict__ meta, const int32_t* __restrict__ n_valid) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n_slots) return;
+  if (i >= n_slots || (n_valid != nullptr && i >= *n_valid)) return;
   int e = ids[i];
   if (expert_map != nullptr) e = expert_map[e];
   if (e >= 0 && e < E_local) atomicAdd(&meta[2 + e], 1);
@@ -207,12 +208,13 @@ __global__ void moe_offsets_kernel(int32_t* __restrict__ meta, int32_t* __restri
 __global__ void moe_scatter_gather_kernel(const int32_t* __restrict__ ids, const int32_t* __restrict__ expert_map,
                                           int n_slots, int top_k, int E_local, int32_t* __restrict__ meta,
                                           int32_t* __restrict__ slot_pos, const __nv_bfloat16* __restrict__ x,
-                                          int64_t ldx, __nv_bfloat16* __restrict__ xs, int H) {
+                                          int64_t ldx, __nv_bfloat16* __restrict__ xs, int H,
+                                          const int32_t* __restrict__ n_valid) {
   const int slot = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (slot >= n_slots) return;
-  int e = ids[slot];
-  if (expert_map != nullptr) e = expert_map[e];
+  int e = (n_valid != nullptr && slot >= *n_valid) ? -1 : ids[slot];
+  if (expert_map != nullptr && e >= 0) e = expert_map[e];
   int pos = -1;
   if (e >= 0 && e < E_local) {
     if (lane == 0) pos = meta[2 + 2 * E_local + e] + atomicAdd(&meta[2 + E_local + e], 1);
@@ -300,20 +302,22 @@ GLLM_EXPORT int gllm_moe_grouped_topk(const void* logits, int64_t ld, const void
 // xs: bf16 [max_tiles*128, H] (caller zero-fills padding rows once; stale finite rows are harmless).
 GLLM_EXPORT int gllm_moe_align_gather(const void* ids, const void* expert_map, int T, int top_k, int E_local,
                                       void* meta, void* tile_expert, int max_tiles, void* slot_pos, const void* x,
-                                      int64_t ldx, void* xs, int H, void* stream) {
+                                      int64_t ldx, void* xs, int H, const void* n_valid, void* stream) {
   const int n_slots = T * top_k;
   if (n_slots <= 0) return 0;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   CUDA_CHECK_RET(cudaMemsetAsync(meta, 0, sizeof(int32_t) * (2 + 3 * E_local + 1), st));
   moe_count_kernel<<<(n_slots + 255) / 256, 256, 0, st>>>(reinterpret_cast<const int32_t*>(ids),
                                                            reinterpret_cast<const int32_t*>(expert_map), n_slots,
-                                                           E_local, reinterpret_cast<int32_t*>(meta));
+                                                           E_local, reinterpret_cast<int32_t*>(meta),
+                                                           reinterpret_cast<const int32_t*>(n_valid));
   moe_offsets_kernel<<<1, 256, 0, st>>>(reinterpret_cast<int32_t*>(meta), reinterpret_cast<int32_t*>(tile_expert),
                                         E_local, max_tiles);
   moe_scatter_gather_kernel<<<(n_slots * 32 + 255) / 256, 256, 0, st>>>(
       reinterpret_cast<const int32_t*>(ids), reinterpret_cast<const int32_t*>(expert_map), n_slots, top_k, E_local,
       reinterpret_cast<int32_t*>(meta), reinterpret_cast<int32_t*>(slot_pos),
-      reinterpret_cast<const __nv_bfloat16*>(x), ldx, reinterpret_cast<__nv_bfloat16*>(xs), H);
+      reinterpret_cast<const __nv_bfloat16*>(x), ldx, reinterpret_cast<__nv_bfloat16*>(xs), H,
+      reinterpret_cast<const int32_t*>(n_valid));
   CUDA_CHECK_RET(cudaGetLastError());
   return 0;
 }

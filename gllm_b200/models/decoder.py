@@ -241,10 +241,9 @@ class DecoderLayer(nn.Module):
         a = self.attn(inp, h, kv_cache, tpc, qkv=qkv)
         h, residual = tpc.row_linear_add_norm(a, _qw(self.attn.o_w, self.attn.o_ws), residual, self.post_norm_w, eps, self.attn.o_b)
         if self.is_moe:
-            partial = self.mlp(tpc.materialize(h), tpc)
             if next_norm_w is None:
-                return tpc.all_reduce(partial), residual
-            return tpc.reduce_add_norm(partial, residual, next_norm_w, eps)
+                return tpc.all_reduce(self.mlp(tpc.materialize(h), tpc)), residual
+            return tpc.moe_add_norm(self.mlp, h, residual, next_norm_w, eps)
         act = self.mlp.act(h, tpc)
         if next_norm_w is None:
             return tpc.row_linear(act, self.mlp.down_weight()), residual
@@ -368,6 +367,10 @@ class CausalLM(nn.Module):
                 p.data.fill_(1.0)
             elif p.dim() == 1:
                 p.data.zero_()
+            elif name.endswith("router_w") or name.endswith("shared_gate_w"):
+                # replicated parameters must be identical on every rank
+                gr = torch.Generator(device="cpu").manual_seed(seed + 31 + len(name))
+                p.data.copy_((torch.randn(p.shape, generator=gr) * 0.3).to(p.dtype))
             elif p.dtype == torch.float8_e4m3fn:
                 step = 1 << 26
                 flat = p.data.view(-1)

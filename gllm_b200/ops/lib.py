@@ -65,8 +65,8 @@ def _declare(lib):
     sig("gllm_mark_seen", [P, I, P, P, I, P])
     sig("gllm_moe_topk_softmax", [P, L, P, P, I, I, I, I, P])
     sig("gllm_moe_grouped_topk", [P, L, P, P, P, I, I, I, I, I, I, I, F, P])
-    sig("gllm_moe_align_gather", [P, P, I, I, I, P, P, I, P, P, L, P, I, P])
-    sig("gllm_moe_grouped_gemm", [P, L, P, P, L, I, I, I, I, P, P, I, P])
+    sig("gllm_moe_align_gather", [P, P, I, I, I, P, P, I, P, P, L, P, I, P, P])
+    sig("gllm_moe_grouped_gemm", [P, L, P, P, L, I, I, I, I, P, P, I, P, P])
     sig("gllm_moe_combine", [P, P, P, P, I, I, I, P])
     sig("gllm_fp8_quant_group", [P, L, P, P, I, I, P])
     sig("gllm_gemm_fp8_block", [P, P, P, P, P, L, I, I, I, P, P])

@@ -61,17 +61,22 @@ def grouped_topk(logits: torch.Tensor, top_k: int, renormalize: bool, n_group: i
     return w, ids
 
 
-def fused_experts(x: torch.Tensor, w13: torch.Tensor, w2: torch.Tensor, topk_w: torch.Tensor,
+def fused_experts(x: torch.Tensor, w13: torch.Tensor, w2: torch.Tensor, topk_w: Optional[torch.Tensor],
                   topk_ids: torch.Tensor, expert_map: Optional[torch.Tensor] = None,
-                  out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """x [T,H]; w13 [E_local, 2I, H] (gate/up rows interleaved per 64); w2 [E_local, H, I]; ids global."""
+                  out: Optional[torch.Tensor] = None, n_valid: Optional[torch.Tensor] = None,
+                  row_dest_fn=None) -> Optional[torch.Tensor]:
+    """x [T,H]; w13 [E_local, 2I, H] (gate/up rows interleaved per 64); w2 [E_local, H, I]; ids global.
+
+    `n_valid` (device int32 scalar): only the first n_valid rows of x are live (EP receive pool).
+    `row_dest_fn(slot_pos, rows)` -> int64 [rows] device table: GEMM2's epilogue then stores every output
+    row straight to that address (peer memory) and the local combine is skipped (returns None)."""
     assert x.dtype == _BF16 and x.stride(1) == 1 and w13.is_contiguous() and w2.is_contiguous()
     t, h = x.shape
     e_local, two_i, _ = w13.shape
     inter = two_i // 2
     k = topk_ids.shape[1]
     dev = x.device
-    if out is None:
+    if out is None and row_dest_fn is None:
         out = torch.empty(t, h, dtype=_BF16, device=dev)
     if t == 0:
         return out
@@ -82,15 +87,21 @@ def fused_experts(x: torch.Tensor, w13: torch.Tensor, w2: torch.Tensor, topk_w: 
     slot_pos = _buf("slot_pos", (t * k,), torch.int32, dev)
     xs = _buf("xs", (rows, h), _BF16, dev, zero=True)
     hbuf = _buf("h", (rows, inter), _BF16, dev)
-    ybuf = _buf("y", (rows, h), _BF16, dev)
     L = _lib.load()
     st = stream_ptr()
     check(L.gllm_moe_align_gather(_p(topk_ids), _p(expert_map), t, k, e_local, _p(meta), _p(tile_expert), max_tiles,
-                                  _p(slot_pos), _p(x), x.stride(0), _p(xs), h, st), "moe_align_gather")
+                                  _p(slot_pos), _p(x), x.stride(0), _p(xs), h, _p(n_valid), st), "moe_align_gather")
     check(L.gllm_moe_grouped_gemm(_p(xs), h, _p(w13), _p(hbuf), inter, max_tiles, two_i, h, e_local,
-                                  _p(tile_expert), _p(meta), 1, st), "moe_grouped_gemm1")
+                                  _p(tile_expert), _p(meta), 1, None, st), "moe_grouped_gemm1")
+    if row_dest_fn is not None:
+        row_dest = row_dest_fn(slot_pos, rows)
+        check(L.gllm_moe_grouped_gemm(_p(hbuf), inter, _p(w2), _p(hbuf), h, max_tiles, h, inter, e_local,
+                                      _p(tile_expert), _p(meta), 0, _p(row_dest), st), "moe_grouped_gemm2_push")
+        _count(6)
+        return None
+    ybuf = _buf("y", (rows, h), _BF16, dev)
     check(L.gllm_moe_grouped_gemm(_p(hbuf), inter, _p(w2), _p(ybuf), h, max_tiles, h, inter, e_local,
-                                  _p(tile_expert), _p(meta), 0, st), "moe_grouped_gemm2")
+                                  _p(tile_expert), _p(meta), 0, None, st), "moe_grouped_gemm2")
     check(L.gllm_moe_combine(_p(ybuf), _p(slot_pos), _p(topk_w), _p(out), t, k, h, st), "moe_combine")
     _count(7)
     return out

@@ -41,6 +41,14 @@ class ReduceNormArgs(ctypes.Structure):
     ]
 
 
+class EpArgs(ctypes.Structure):
+    """Mirror of `EpArgs` in csrc/comm/ep_a2a.cu."""
+    _fields_ = [("recv_x", c_void_p * MAX_PEERS), ("recv_e", c_void_p * MAX_PEERS),
+                ("recv_src", c_void_p * MAX_PEERS), ("ctrl", c_void_p * MAX_PEERS), ("comb", c_void_p * MAX_PEERS),
+                ("state", c_void_p), ("ep", c_int), ("rank", c_int), ("experts_per_rank", c_int), ("top_k", c_int),
+                ("H", c_int), ("r_max", c_int)]
+
+
 MAX_BLOCKS = 256   # kMaxBlocks in csrc/comm/tp_fused.cu (128-row blocks per gather buffer)
 SMALL_T = 64       # forwards with <= this many tokens use the NCCL strategy (see begin_forward)
 
@@ -54,6 +62,14 @@ def _declare(L):
     L.gllm_wait_ag_flags.restype = c_int
     L.gllm_tp_state_bytes.argtypes = []
     L.gllm_tp_state_bytes.restype = c_int
+    L.gllm_ep_state_bytes.argtypes = []
+    L.gllm_ep_state_bytes.restype = c_int
+    L.gllm_ep_dispatch.argtypes = [ctypes.POINTER(EpArgs), c_void_p, c_int64, c_void_p, c_int, c_void_p]
+    L.gllm_ep_dispatch.restype = c_int
+    L.gllm_ep_row_dest.argtypes = [ctypes.POINTER(EpArgs), c_void_p, c_void_p, c_int, c_void_p]
+    L.gllm_ep_row_dest.restype = c_int
+    L.gllm_ep_combine.argtypes = [ctypes.POINTER(EpArgs), c_void_p, c_void_p, c_int, c_void_p]
+    L.gllm_ep_combine.restype = c_int
 
 
 class FusedTPComm(TPComm):
@@ -111,6 +127,8 @@ class FusedTPComm(TPComm):
         self.ag_call = 0
         self.small = False
         self.cur_ag = None  # (ag_idx, tensor view) produced by the last reduce_norm
+        self.ep = None      # expert-parallel all-to-all buffers, created by the first MoE block
+        self.ep_call = 0
         logger.info("fused TP: %d MB symmetric buffer per rank, peers mapped over NVLink", total >> 20)
 
     # -------------------------------------------------------------------------------------------
@@ -243,10 +261,127 @@ class FusedTPComm(TPComm):
         sm100._count()
         return self._reduce_norm(parity, self._rows_valid(), None, residual is not None, norm_w, eps)
 
+    # -------------------------------------------------------------------------------------------
+    # expert-parallel all-to-all (csrc/comm/ep_a2a.cu)
+    # -------------------------------------------------------------------------------------------
+    def _ep_setup(self, experts):
+        """Collective (every rank reaches its first MoE block together, in the eager profile run)."""
+        import torch.distributed._symmetric_memory as symm
+        tp, H, k = self.tp_size, self.H, experts.top_k
+        per = experts.num_experts // tp
+        e_local_max = experts.num_experts - (tp - 1) * per
+        r_max = self.max_tokens * min(k, e_local_max)
+        r_max = (r_max + 127) // 128 * 128
+        comb_rows = self.rpr_max * k
+        sz = {"recv_x": r_max * H * 2, "recv_e": r_max * 4, "recv_src": r_max * 4, "comb": comb_rows * H * 2,
+              "ctrl": 256}
+        off, cur = [], 0
+        for _ in range(2):
+            o = {}
+            for name, n in sz.items():
+                o[name] = cur
+                cur += (n + 255) // 256 * 256
+            off.append(o)
+        blob = symm.empty(cur, dtype=torch.uint8, device=self.device)
+        blob.zero_()
+        hdl = symm.rendezvous(blob, self.group.group_name)
+        bases = [int(p) for p in hdl.buffer_ptrs]
+        state = torch.zeros(self.L.gllm_ep_state_bytes(), dtype=torch.uint8, device=self.device)
+        args = []
+        for par in range(2):
+            a = EpArgs()
+            for p in range(tp):
+                a.recv_x[p] = bases[p] + off[par]["recv_x"]
+                a.recv_e[p] = bases[p] + off[par]["recv_e"]
+                a.recv_src[p] = bases[p] + off[par]["recv_src"]
+                a.ctrl[p] = bases[p] + off[par]["ctrl"]
+                a.comb[p] = bases[p] + off[par]["comb"]
+            a.state = state.data_ptr()
+            a.ep, a.rank, a.experts_per_rank, a.top_k, a.H, a.r_max = tp, self.tp_rank, per, k, H, r_max
+            args.append(a)
+
+        def view(par, name, dtype, shape):
+            o = off[par][name]
+            n = 1
+            for d in shape:
+                n *= d
+            return blob[o: o + n * torch.empty((), dtype=dtype).element_size()].view(dtype).view(*shape)
+
+        self.ep = dict(
+            blob=blob, hdl=hdl, state=state, args=args, r_max=r_max, k=k,
+            recv_x=[view(p, "recv_x", torch.bfloat16, (r_max, H)) for p in range(2)],
+            recv_e=[view(p, "recv_e", torch.int32, (r_max, 1)) for p in range(2)],
+            n_valid=[view(p, "ctrl", torch.int32, (1,)) for p in range(2)],
+            out=torch.zeros(self.rpr_max, H, dtype=torch.bfloat16, device=self.device),
+            row_dest=torch.zeros(r_max + 128 * (e_local_max + 1), dtype=torch.int64, device=self.device))
+        torch.cuda.synchronize()
+        dist.barrier(group=self.group)
+        logger.info("EP all-to-all: %d MB symmetric pool per rank (%d rows x2)", cur >> 20, r_max)
+
+    def can_a2a(self, block) -> bool:
+        ex = getattr(block, "experts", None)
+        return (not self.small and ex is not None and ex.use_ep and getattr(block, "shared", None) is None
+                and ex.w13.is_cuda and ex.top_k <= 63)
+
+    def moe_add_norm(self, block, h, residual, norm_w, eps):
+        """MoE block + residual add + next RMSNorm. Routed experts only (no shared expert) and EP:
+        dispatch -> grouped GEMMs whose epilogue returns the rows -> combine, all over peer memory."""
+        if not self.can_a2a(block):
+            return super().moe_add_norm(block, h, residual, norm_w, eps)
+        from gllm_b200.ops import sm100, sm100_moe
+        ex = block.experts
+        if self.ep is None:
+            self._ep_setup(ex)
+        ep = self.ep
+        assert ep["k"] == ex.top_k
+        par = self.ep_call % 2
+        self.ep_call += 1
+        a = ep["args"][par]
+        rv, r0 = self._rows_valid(), self.tp_rank * self.rpr
+        st = stream_ptr()
+        if rv > 0:
+            w, ids = ex.route(h[r0:r0 + rv])   # own rows of the gather buffer are local writes: no flag wait
+            xs = h[r0:r0 + rv]
+            check(self.L.gllm_ep_dispatch(ctypes.byref(a), xs.data_ptr(), xs.stride(0), ids.data_ptr(), rv, st),
+                  "ep_dispatch")
+        else:
+            w = None
+            check(self.L.gllm_ep_dispatch(ctypes.byref(a), None, 0, None, 0, st), "ep_dispatch")
+
+        def row_dest_fn(slot_pos, rows):
+            rd = ep["row_dest"]
+            assert rows <= rd.numel()
+            check(self.L.gllm_ep_row_dest(ctypes.byref(a), slot_pos.data_ptr(), rd.data_ptr(), rows, st),
+                  "ep_row_dest")
+            return rd
+
+        sm100_moe.fused_experts(ep["recv_x"][par], ex.w13, ex.w2, None, ep["recv_e"][par], None,
+                                n_valid=ep["n_valid"][par], row_dest_fn=row_dest_fn)
+        out = ep["out"]
+        check(self.L.gllm_ep_combine(ctypes.byref(a), w.data_ptr() if w is not None else None, out.data_ptr(), rv,
+                                     st), "ep_combine")
+        sm100._count(6)
+        # `out` holds this rank's rows only; rs_reduce_norm indexes a full [T, H] tensor by global row
+        shifted = _ShiftedRows(out, r0)
+        return self._reduce_norm(0, 0, shifted, residual is not None, norm_w, eps)
+
     def row_linear(self, x, w, bias=None):
         if self.small:
             return super().row_linear(x, w, bias)
         raise NotImplementedError("fused TP is used with pp_size == 1 (no un-normalised stage boundary)")
+
+
+class _ShiftedRows:
+    """Presents a rank-local [rows, H] tensor as if it were rows [r0, r0+rows) of a full tensor."""
+
+    def __init__(self, t, r0):
+        self._t, self._r0 = t, r0
+
+    def stride(self, i):
+        return self._t.stride(i)
+
+    def data_ptr(self):
+        return self._t.data_ptr() - self._r0 * self._t.stride(0) * self._t.element_size()
 
 
 class _FakeOut:

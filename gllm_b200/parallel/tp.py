@@ -63,6 +63,13 @@ class TPComm:
             return normed, partial
         return Fn.rmsnorm(partial, norm_w, eps, residual)
 
+    def moe_add_norm(self, block, h: torch.Tensor, residual: Optional[torch.Tensor], norm_w: torch.Tensor,
+                     eps: float):
+        """MoE block (TP-partial output) + reduce + residual add + next RMSNorm. The fused strategy
+        overrides this with the all-to-all dispatch/combine form for EP models."""
+        partial = block(self.materialize(h), self)
+        return self.reduce_add_norm(partial, residual, norm_w, eps)
+
     def row_linear_add_norm(self, x: torch.Tensor, w: torch.Tensor, residual: Optional[torch.Tensor],
                             norm_w: torch.Tensor, eps: float, bias: Optional[torch.Tensor] = None):
         # bias is added once (rank 0) like the reference (gllm/layers/linear.py:230-258)

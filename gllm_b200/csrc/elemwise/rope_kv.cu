@@ -26,8 +26,20 @@ struct RopeParams {
   float eps;
   __nv_bfloat16* k_cache;
   __nv_bfloat16* v_cache;
-  int sec0, sec1, page_size;
+  int sec0, sec1, page_size;  // sec0 > 0: chunked M-RoPE [T|H|W]; sec0 < 0: interleaved (H = -sec0, W = sec1)
+  int64_t pos_stride;         // row stride of a [3, T] positions tensor
 };
+
+// which of the (t, h, w) position rows rotary pair i uses
+__device__ __forceinline__ int mrope_axis(int i, int sec0, int sec1) {
+  if (sec0 > 0) return i < sec0 ? 0 : (i < sec0 + sec1 ? 1 : 2);
+  if (sec0 < 0) {
+    const int r = i % 3;
+    if (r == 1 && i < -sec0 * 3) return 1;
+    if (r == 2 && i < sec1 * 3) return 2;
+  }
+  return 0;
+}
 
 template <int C>  // elements per lane, D = 32 * C
 __global__ void rope_kv_kernel(const RopeParams p) {
@@ -40,8 +52,8 @@ __global__ void rope_kv_kernel(const RopeParams p) {
   const int n_heads = p.Hq + p.Hkv + ((p.v != nullptr && p.slots != nullptr) ? p.Hkv : 0);
 
   int pos[3];
-  if (p.sec0 > 0) {
-    pos[0] = p.positions[t]; pos[1] = p.positions[p.T + t]; pos[2] = p.positions[2 * p.T + t];
+  if (p.sec0 != 0) {
+    pos[0] = p.positions[t]; pos[1] = p.positions[p.pos_stride + t]; pos[2] = p.positions[2 * p.pos_stride + t];
   } else {
     pos[0] = pos[1] = pos[2] = p.positions != nullptr ? p.positions[t] : 0;
   }
@@ -89,7 +101,7 @@ __global__ void rope_kv_kernel(const RopeParams p) {
 #pragma unroll
             for (int e = 0; e < C; ++e) {
               const int i = (e0 + e) % half;
-              const int ps = p.sec0 > 0 ? (i < p.sec0 ? pos[0] : (i < p.sec0 + p.sec1 ? pos[1] : pos[2])) : pos[0];
+              const int ps = pos[mrope_axis(i, p.sec0, p.sec1)];
               const float c = p.cos_sin[static_cast<size_t>(ps) * p.rot + i];
               const float s = p.cos_sin[static_cast<size_t>(ps) * p.rot + half + i];
               x[e] = lo ? x[e] * c - y[e] * s : x[e] * c + y[e] * s;
@@ -100,7 +112,7 @@ __global__ void rope_kv_kernel(const RopeParams p) {
 #pragma unroll
             for (int e = 0; e < C; e += 2) {
               const int i = (e0 + e) >> 1;
-              const int ps = p.sec0 > 0 ? (i < p.sec0 ? pos[0] : (i < p.sec0 + p.sec1 ? pos[1] : pos[2])) : pos[0];
+              const int ps = pos[mrope_axis(i, p.sec0, p.sec1)];
               const float c = p.cos_sin[static_cast<size_t>(ps) * p.rot + i];
               const float s = p.cos_sin[static_cast<size_t>(ps) * p.rot + half + i];
               const float a = x[e], b = x[e + 1];
@@ -143,7 +155,7 @@ GLLM_EXPORT int gllm_rope_kv_write(void* q, int64_t q_ts, int64_t q_hs, int Hq, 
                                    const void* q_norm_w, const void* k_norm_w, const void* cos_sin, int D,
                                    int rot, int neox, int T, const void* positions, const void* slots,
                                    float eps, void* k_cache, void* v_cache, int sec0, int sec1,
-                                   int page_size, void* stream) {
+                                   int page_size, int64_t pos_stride, void* stream) {
   if (T <= 0) return 0;
   RopeParams p;
   p.q = reinterpret_cast<__nv_bfloat16*>(q); p.q_ts = q_ts; p.q_hs = q_hs; p.Hq = Hq;
@@ -158,7 +170,7 @@ GLLM_EXPORT int gllm_rope_kv_write(void* q, int64_t q_ts, int64_t q_hs, int Hq, 
   p.eps = eps;
   p.k_cache = reinterpret_cast<__nv_bfloat16*>(k_cache);
   p.v_cache = reinterpret_cast<__nv_bfloat16*>(v_cache);
-  p.sec0 = sec0; p.sec1 = sec1; p.page_size = page_size;
+  p.sec0 = sec0; p.sec1 = sec1; p.page_size = page_size; p.pos_stride = pos_stride;
   const int C = D / 32;
   if (D % 64 != 0 || (rot > 0 && ((rot / 2) % C != 0 || rot > D))) {
     fprintf(stderr, "[gllm_b200] rope_kv_write: unsupported D=%d rot=%d\n", D, rot);

@@ -206,6 +206,9 @@ class LLM:
                        mm_contents)
         if output_len is None:
             seq.output_len = min(4096, self.model_max_length - len(token_ids))
+        if mm_contents:
+            from gllm_b200.models.multimodal import MMInfo, prepare_mm_sequence
+            prepare_mm_sequence(seq, MMInfo.from_config(self.loader.config))
         seq.arrival_time = time.time()
         return seq
 
@@ -285,9 +288,11 @@ class LLM:
     # -------------------------------------------------------------------------------------------
     def generate(self, prompts: Optional[List[str]] = None, tokens: Optional[List[List[int]]] = None,
                  output_lens: Optional[List[int]] = None, temperature=None, top_p=None, top_k=None,
-                 repetition_penalty=None, ignore_eos: bool = False, progress: bool = False) -> List[Sequence]:
+                 repetition_penalty=None, ignore_eos: bool = False, progress: bool = False,
+                 mm_contents: Optional[List[Optional[dict]]] = None) -> List[Sequence]:
         """Batch generation; returns the finished `Sequence`s in request order with `.prompt`,
-        `.output`, `.token_ids` (reference: gllm/llm_engine.py:343-378)."""
+        `.output`, `.token_ids` (reference: gllm/llm_engine.py:343-378). `mm_contents[i]` (VL models) is
+        the processor output of request i: pixel_values / image_grid_thw [/ pixel_values_videos ...]."""
         if self.worker is not None and self.worker.rank != 0:
             return self._serve_until_stop()
         if tokens is None:
@@ -300,7 +305,8 @@ class LLM:
             if not self.check_seq_length(toks, ol):
                 raise ValueError(f"request {i}: prompt ({len(toks)}) + output ({ol}) exceeds the model max length "
                                  f"{self.model_max_length}")
-            seqs.append(self.allocate_seq(toks, ol, ignore_eos, temperature, top_p, top_k, repetition_penalty))
+            seqs.append(self.allocate_seq(toks, ol, ignore_eos, temperature, top_p, top_k, repetition_penalty,
+                                          mm_contents[i] if mm_contents is not None else None))
         self.add_requests(seqs)
         base = len(self.finished)
         bar = None

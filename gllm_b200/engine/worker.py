@@ -156,7 +156,8 @@ class Worker(ProfilerMixin):
         if entries:
             did = True
             self.batch_counter += 1
-            batch = build_batch(entries, self.cfg.page_size, self.runner.spec.vocab_size, self.batch_counter)
+            batch = build_batch(entries, self.cfg.page_size, self.runner.spec.vocab_size, self.batch_counter,
+                                mrope=self.runner.input_data.mrope)
             if self.comm is not None:
                 self.comm.send_batch(batch)
             res = self.runner.step(batch)

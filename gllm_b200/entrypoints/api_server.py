@@ -165,9 +165,10 @@ def build_app(engine):
         mm_contents = None
         try:
             if llm.loader.use_mm:
-                from gllm_b200.models.multimodal import extract_mm_contents
-                mm_contents = await _in_thread(extract_mm_contents, llm, request.messages)
-            token_ids = await _in_thread(llm.encode, None, True, request.messages)
+                from gllm_b200.models.multimodal import encode_mm
+                token_ids, mm_contents = await _in_thread(encode_mm, llm, request.messages)
+            else:
+                token_ids = await _in_thread(llm.encode, None, True, request.messages)
         except Exception as e:  # noqa: BLE001
             return _error(f"cannot encode messages: {e}")
         if not llm.check_seq_length(token_ids, request.output_len()):

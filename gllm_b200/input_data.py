@@ -97,7 +97,7 @@ def build_batch(entries, page_size: int, vocab_size: int, batch_id: int = 0, mro
     np.cumsum(q_lens, out=qsl[1:])
     t = int(qsl[-1])
     tokens = np.empty(t, dtype=np.int32)
-    positions = np.empty(t, dtype=np.int32)
+    positions = np.empty((3, t) if mrope else t, dtype=np.int32)
     slots = np.empty(t, dtype=np.int32)
     max_blocks = int((seq_lens.max() + page_size - 1) // page_size) if b else 1
     block_table = np.zeros((b, max_blocks), dtype=np.int32)
@@ -115,12 +115,20 @@ def build_batch(entries, page_size: int, vocab_size: int, batch_id: int = 0, mro
         s0 = e.start
         if e.n == 1:
             tokens[a] = seq.token_ids[s0]
-            positions[a] = s0
+            if mrope:
+                positions[:, a] = (s0 + seq.mrope_delta) if (not seq.mm_state or s0 >= seq.prompt_len) \
+                    else seq.mm_state["positions"][:, s0]
+            else:
+                positions[a] = s0
             slots[a] = pt[s0 // page_size] * page_size + s0 % page_size
         else:
             tokens[a:z] = seq.token_ids[s0:s0 + e.n]
             pos = np.arange(s0, s0 + e.n, dtype=np.int32)
-            positions[a:z] = pos
+            if mrope:
+                from gllm_b200.models.multimodal import seq_positions
+                positions[:, a:z] = seq_positions(seq, s0, e.n)
+            else:
+                positions[a:z] = pos
             slots[a:z] = pt[pos // page_size] * page_size + pos % page_size
         if e.emits:
             emit_seq.append(i)
@@ -143,8 +151,10 @@ def build_batch(entries, page_size: int, vocab_size: int, batch_id: int = 0, mro
                 else:
                     seen_rows.append(np.array([seq.slot], dtype=np.int32))
                     seen_tokens.append(np.array([seq.token_ids[s0]], dtype=np.int32))
+    mm = None
     if mrope:
-        positions = np.broadcast_to(positions, (3, t)).copy()
+        from gllm_b200.models.multimodal import batch_mm_payload
+        mm = batch_mm_payload(entries, qsl)
     return BatchArrays(
         tokens=tokens, positions=positions, slot_mapping=slots, block_table=block_table, seq_lens=seq_lens,
         query_start_loc=qsl, logits_idx=np.asarray(logits_idx, dtype=np.int32),
@@ -155,7 +165,7 @@ def build_batch(entries, page_size: int, vocab_size: int, batch_id: int = 0, mro
         max_seq_len=int(seq_lens.max()) if b else 0, all_greedy=all_greedy, need_penalty=need_penalty,
         seen_rows=np.concatenate(seen_rows) if seen_rows else None,
         seen_tokens=np.concatenate(seen_tokens) if seen_tokens else None,
-        clear_slots=np.asarray(clear_slots, dtype=np.int32) if clear_slots else None, batch_id=batch_id)
+        clear_slots=np.asarray(clear_slots, dtype=np.int32) if clear_slots else None, batch_id=batch_id, mm=mm)
 
 
 class InputData:

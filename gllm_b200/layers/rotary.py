@@ -74,7 +74,9 @@ def build_rope(head_dim: int, max_position: int, base: float, rope_scaling: Opti
     if rope_scaling:
         kind = rope_scaling.get("rope_type", rope_scaling.get("type", "default"))
         if "mrope_section" in rope_scaling:
-            spec.mrope_section = list(rope_scaling["mrope_section"])
+            spec.mrope_section = list(rope_scaling["mrope_section"])[:3]
+            if rope_scaling.get("mrope_interleaved"):
+                spec.mrope_section.append(1)  # 4th entry flags the interleaved layout
         if kind == "linear":
             factor = rope_scaling["factor"]
             inv_freq = _default_inv_freq(rot, base) / factor

@@ -107,7 +107,8 @@ class PrefixMemoryManager(MemoryManager):
         toks = seq.token_ids
         while len(hs) < upto_pages:
             i = len(hs)
-            prev = hs[-1] if hs else 0x9E3779B97F4A7C15
+            # multimodal prompts share placeholder ids: salt the chain with a digest of the pixels
+            prev = hs[-1] if hs else 0x9E3779B97F4A7C15 ^ ((seq.mm_state or {}).get("salt", 0))
             hs.append(hash((prev, tuple(toks[i * ps:(i + 1) * ps]))))
 
     # -- allocation -----------------------------------------------------------------------------

@@ -90,7 +90,8 @@ class ModelRunner:
         t0 = time.time()
         self.model = self.loader.load_model(self.device, progress)
         self.spec = self.model.spec
-        self.tpc = make_tp_comm(fused=(cfg.tp_mode == "fused" and getattr(self.spec, "quant", None) is None),
+        self.tpc = make_tp_comm(fused=(cfg.tp_mode == "fused" and getattr(self.spec, "quant", None) is None
+                                       and not getattr(self.model, "num_deepstack", 0)),
                                 max_tokens=self.max_num_batched_tokens,
                                 hidden_size=self.spec.hidden_size, dtype=self.spec.dtype, device=self.device) \
             if cfg.tp_size > 1 else make_tp_comm(False)

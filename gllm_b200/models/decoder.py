@@ -302,7 +302,7 @@ class CausalLM(nn.Module):
 
     def forward(self, inp, kv_cache, tpc: TPComm, hidden: Optional[torch.Tensor] = None,
                 residual: Optional[torch.Tensor] = None, inputs_embeds: Optional[torch.Tensor] = None,
-                recv_tiles=None):
+                recv_tiles=None, deepstack=None):
         """First stage: tokens -> ... ; later stages: (hidden, residual) from the previous stage.
         Returns (hidden, residual): on the last stage `hidden` is the final-normed activation."""
         eps = self.spec.rms_eps
@@ -345,7 +345,13 @@ class CausalLM(nn.Module):
                 nxt = self.layers[i + 1].input_norm_w
             else:
                 nxt = self.final_norm_w if self.is_last else None
-            if i == 0 and qkv0 is not None:
+            if deepstack is not None and i < len(deepstack[1]):
+                # DeepStack (Qwen3-VL): intermediate ViT features are added to the block output at the
+                # visual token rows before the next block's norm (reference: models/qwen3_vl.py:525-568)
+                out, residual = layer(inp, h, residual, kv_cache, tpc, None)
+                out.index_add_(0, deepstack[0], deepstack[1][i])
+                h, residual = Fn.rmsnorm(out, nxt, eps, residual)
+            elif i == 0 and qkv0 is not None:
                 h, residual = layer(inp, h, residual, kv_cache, tpc, nxt, qkv=qkv0)
             else:
                 h, residual = layer(inp, h, residual, kv_cache, tpc, nxt)

@@ -138,9 +138,13 @@ def rope_kv_write(q: torch.Tensor, k: torch.Tensor, v: Optional[torch.Tensor], p
         if mrope_section is not None and positions.dim() == 2:
             # positions [3, T]; pair index i picks the section's position row
             sec = torch.zeros(half, dtype=torch.long, device=positions.device)
-            s0, s1 = mrope_section[0], mrope_section[1]
-            sec[s0:s0 + s1] = 1
-            sec[s0 + s1:] = 2
+            if len(mrope_section) > 3 and mrope_section[3]:   # interleaved THWTHW.. (Qwen3-VL)
+                sec[1:mrope_section[1] * 3:3] = 1
+                sec[2:mrope_section[2] * 3:3] = 2
+            else:
+                s0, s1 = mrope_section[0], mrope_section[1]
+                sec[s0:s0 + s1] = 1
+                sec[s0 + s1:] = 2
             cs = cos_sin.to(positions.device)[positions.long()]  # [3, T, rot]
             idx = sec.view(1, 1, half).expand(1, positions.shape[1], half)
             cos = torch.gather(cs[..., :half], 0, idx)[0]

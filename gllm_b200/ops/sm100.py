@@ -192,15 +192,24 @@ def rope_kv_write(q: torch.Tensor, k: torch.Tensor, v: Optional[torch.Tensor], p
         assert cos_sin.dtype == torch.float32 and cos_sin.is_contiguous()
     assert positions.dtype == torch.int32
     sec0 = sec1 = 0
+    pos_stride = 0
     if mrope_section is not None and positions.dim() == 2:
-        sec0, sec1 = int(mrope_section[0]), int(mrope_section[1])
-        assert positions.is_contiguous()
+        # chunked [T|H|W] sections (Qwen2.5-VL) or, flagged by a 4th entry "interleaved", THWTHW.. (Qwen3-VL)
+        if len(mrope_section) > 3 and mrope_section[3]:
+            sec0, sec1 = -int(mrope_section[1]), int(mrope_section[2])
+        else:
+            sec0, sec1 = int(mrope_section[0]), int(mrope_section[1])
+        assert positions.stride(1) == 1
+        pos_stride = positions.stride(0)
+    elif positions.dim() == 2:
+        positions = positions[0]
     L = _lib.load()
     rc = L.gllm_rope_kv_write(
         _p(q), q.stride(0), q.stride(1), hq, _p(k), k.stride(0), k.stride(1), hkv,
         _p(v), v.stride(0) if v is not None else 0, v.stride(1) if v is not None else 0,
         _p(q_norm_w), _p(k_norm_w), _p(cos_sin), d, rot_dim if cos_sin is not None else 0, 1 if neox else 0, t,
-        _p(positions), _p(slots), float(eps), _p(k_cache), _p(v_cache), sec0, sec1, page_size, stream_ptr())
+        _p(positions), _p(slots), float(eps), _p(k_cache), _p(v_cache), sec0, sec1, page_size, pos_stride,
+        stream_ptr())
     check(rc, "rope_kv_write")
     _count()
 

@@ -78,6 +78,8 @@ class Sequence:
         self.scheduled_token_num = 0
         self.page_table = []
         self.page_hashes = []
+        if self.mm_state:
+            self.mm_state["sent"] = False  # the vision embeddings must be recomputed too
 
     def detokenize_inc(self, tokenizer) -> str:
         """Incremental detokenisation; holds back while the tail decodes to U+FFFD."""

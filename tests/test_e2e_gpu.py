@@ -50,3 +50,42 @@ def test_graph_and_eager_agree():
     t2, _, st = _gen("cuda", True, prompts, 8, state=params)
     assert st["graph_steps"] > 0
     assert t1 == t2
+
+
+def test_qwen3_vl_gpu_matches_cpu_engine():
+    """Qwen3-VL (vision tower, interleaved M-RoPE kernel path, DeepStack) on the GPU vs the fp32 CPU engine."""
+    import numpy as np
+    from gllm_b200 import LLM
+    img, vstart = 290, 292
+    cfg = {"architectures": ["Qwen3VLForConditionalGeneration"], "image_token_id": img, "video_token_id": 291,
+           "vision_start_token_id": vstart, "tie_word_embeddings": False,
+           "text_config": dict(hidden_size=256, num_hidden_layers=4, num_attention_heads=4, num_key_value_heads=2,
+                               head_dim=64, intermediate_size=512, vocab_size=512, max_position_embeddings=512,
+                               rms_norm_eps=1e-6, eos_token_id=1,
+                               rope_parameters={"rope_type": "default", "mrope_section": [12, 10, 10],
+                                                "mrope_interleaved": True, "rope_theta": 10000.0}),
+           "vision_config": dict(depth=3, hidden_size=64, num_heads=2, intermediate_size=128, out_hidden_size=256,
+                                 patch_size=16, spatial_merge_size=2, temporal_patch_size=2,
+                                 num_position_embeddings=16, deepstack_visual_indexes=[0, 1], in_channels=3)}
+    grids = [(1, 4, 6)]
+    g = torch.Generator().manual_seed(0)
+    pix = torch.randn(24, 3 * 2 * 16 * 16, generator=g).numpy()
+    ids = [5, 17, 99, vstart] + [img] * 6 + [7, 8, 45, 46]
+    mm = {"pixel_values": pix, "image_grid_thw": np.asarray(grids)}
+    outs, params = {}, None
+    cfg["torch_dtype"] = "bfloat16"
+    for dev in ("cpu", "cuda"):
+        torch.manual_seed(11)
+        llm = LLM(cfg, load_format="dummy", device=dev, maxp=64, maxd=16, model_max_length=256, log_stats=False,
+                  num_cpu_pages=64, num_gpu_pages=64, max_cuda_graph_bs=4)
+        model = llm.worker.runner.model
+        if params is None:
+            params = [(n, p.detach().cpu().clone()) for n, p in model.named_parameters()]
+        else:
+            for (n, p), (_, q) in zip(model.named_parameters(), params):
+                p.data.copy_(q.to(p.device))
+        o = llm.generate(tokens=[ids, ids[:3]], output_lens=[6, 6], ignore_eos=True, mm_contents=[mm, None])
+        outs[dev] = [s.token_ids[-6:] for s in o]
+        llm.shutdown()
+    # bf16 kernels vs the PyTorch oracle path on a random model: the first generated tokens must agree
+    assert [x[0] for x in outs["cpu"]] == [x[0] for x in outs["cuda"]], outs

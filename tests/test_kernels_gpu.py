@@ -131,16 +131,18 @@ def test_rope_kv_write(d, rot, neox, qk_norm):
     assert torch.equal(vc, vc_r)
 
 
-def test_rope_mrope():
+@pytest.mark.parametrize("sec", [[16, 24, 24], [24, 20, 20, 1]])   # chunked (Qwen2.5-VL) / interleaved (Qwen3-VL)
+@pytest.mark.parametrize("strided", [False, True])
+def test_rope_mrope(sec, strided):
     from gllm_b200.ops import sm100
     torch.manual_seed(5)
     t, hq, hkv, d = 40, 4, 2, 128
     q = torch.randn(t, hq, d, device=_dev()).bfloat16()
     k = torch.randn(t, hkv, d, device=_dev()).bfloat16()
     q_r, k_r = q.clone(), k.clone()
-    pos = torch.randint(0, 300, (3, t), device=_dev(), dtype=torch.int32)
+    pos = torch.randint(0, 300, (3, t + 24), device=_dev(), dtype=torch.int32)
+    pos = pos[:, :t] if strided else pos[:, :t].contiguous()   # the runner passes a view of a [3, max_tokens] buffer
     cs = ref.build_cos_sin_cache(d, 512, 1e6).to(_dev())
-    sec = [16, 24, 24]
     sm100.rope_kv_write(q, k, None, pos, cs, d, True, None, None, 1e-6, None, None, None, mrope_section=sec)
     ref.rope_kv_write(q_r, k_r, None, pos, cs, d, True, None, None, 1e-6, None, None, None, mrope_section=sec)
     assert _rel_err(q, q_r) < 8e-3 and _rel_err(k, k_r) < 8e-3

@@ -70,16 +70,16 @@ __global__ void ep_dispatch_kernel(const __nv_bfloat16* __restrict__ x, int64_t 
       peers.recv_src[owner][r] = static_cast<int32_t>(pack_src(rank, slot - tok * top_k, tok));
     }
   }
-  __threadfence_system();
   __syncthreads();
   if (threadIdx.x == 0) {
+    __threadfence_system();  // cumulative over the CTA's peer stores (ordered before by the barrier)
     const uint32_t t = atomicAdd(&st->ticket, 1u);
     if (t == gridDim.x - 1) {
       st->ticket = 0;
       const uint32_t call = st->calls + 1;
       st->calls = call;
       __threadfence_system();
-      for (int p = 0; p < ep; ++p) st_release_sys(peers.ctrl[p] + kCtrlDispatch + rank, call);
+      for (int p = 0; p < ep; ++p) st_relaxed_sys(peers.ctrl[p] + kCtrlDispatch + rank, call);
     }
   }
 }
@@ -109,7 +109,7 @@ __global__ void ep_signal_kernel(const EpPeers peers, int ep, int rank, const Ep
   if (threadIdx.x == 0) {
     __threadfence_system();
     const uint32_t call = st->calls;
-    for (int p = 0; p < ep; ++p) st_release_sys(peers.ctrl[p] + kCtrlReturn + rank, call);
+    for (int p = 0; p < ep; ++p) st_relaxed_sys(peers.ctrl[p] + kCtrlReturn + rank, call);
   }
 }
 

@@ -156,14 +156,15 @@ __global__ void rs_reduce_norm_kernel(const ReduceNormParams p) {
     }
   }
   // publish this row: one arrival on the row's 128-row block counter of every rank
-  __threadfence_system();
+  // (CTA barrier, then ONE system fence by the signalling thread: cumulative over the CTA's stores)
   __syncthreads();
   if (threadIdx.x == 0) {
     if (row < p.rows_valid && p.norm_w != nullptr) {
+      __threadfence_system();
       const int blk = (p.rank * p.rows_per_rank + row) / kFlagBlockRows;
       for (int d = 0; d < p.tp; ++d) {
         const int peer = (p.rank + d) % p.tp;
-        red_add_release_sys(p.flag_peers[peer] + blk, 1u);
+        red_add_relaxed_sys(p.flag_peers[peer] + blk, 1u);
       }
     }
     const uint32_t old = atomicAdd(&p.st->ticket[0], 1u);
@@ -199,9 +200,11 @@ __global__ void push_partial_rows_kernel(const __nv_bfloat16* __restrict__ x, in
   __nv_bfloat16* dst = stage_peers[owner] + (static_cast<size_t>(rank) * rows_per_rank + rl) * H;
   const __nv_bfloat16* src = x + static_cast<size_t>(row) * ldx;
   for (int i = threadIdx.x * 8; i < H; i += blockDim.x * 8) st_v4(dst + i, *reinterpret_cast<const uint4*>(src + i));
-  __threadfence_system();
   __syncthreads();
-  if (threadIdx.x == 0) red_add_release_sys(cnt_peers[owner] + rank, 1u);
+  if (threadIdx.x == 0) {
+    __threadfence_system();
+    red_add_relaxed_sys(cnt_peers[owner] + rank, 1u);
+  }
 }
 
 // Block the stream until the shards of a gather buffer have been published for the current epoch

@@ -44,7 +44,6 @@ struct GemmParams {
   uint32_t rs_inc;
   __nv_bfloat16* peer_out[kMaxPeers];
   uint32_t* peer_cnt[kMaxPeers];
-  uint32_t prefetch_kb;
   // grouped (MoE) mode: M tile t multiplies the weight slab of expert tile_expert[t]
   const int32_t* tile_expert;
   const int32_t* num_m_tiles_ptr;  // device scalar: number of live M tiles
@@ -52,6 +51,11 @@ struct GemmParams {
   // per-row destination table (EP combine push): row r of C is stored at row_dest[r] (any rank's memory
   // mapped over NVLink); 0 = padding row, not stored. comm/ep_a2a.cu builds the table.
   const int64_t* row_dest;
+  // split-K (decode-sized M): unit = (tile, k-slice); partials go through an fp32 workspace in a
+  // thread-private layout, the last-arriving CTA of a tile sums them in slice order and runs the epilogue
+  int split_k;
+  float* ws;
+  uint32_t* tile_cnt;
 };
 
 template <int BN>
@@ -59,12 +63,14 @@ struct GemmCfg {
   static constexpr int kABytes = kBlockM * kBlockK * 2;
   static constexpr int kBBytes = BN * kBlockK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kSmemBudget = 220 * 1024;
+  // epilogue staging: 4 warps x 32 rows x 64 output columns (bf16) + 4 x 32 destination row pointers
+  static constexpr int kEpiBytes = 4 * 32 * 128 + 4 * 32 * 8 + 16;
+  static constexpr int kSmemBudget = 220 * 1024 - kEpiBytes;
   static constexpr int kStagesRaw = kSmemBudget / kStageBytes;
   static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
   static constexpr int kTmemCols = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
   // barriers: full[S], empty[S], tmem_full[2], tmem_empty[2] + tmem ptr
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 + kEpiBytes;
 };
 
 template <int BN, int EPI>
@@ -81,6 +87,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   uint64_t* tmem_full = empty_bar + S;
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  uint8_t* epi_smem = smem + S * Cfg::kStageBytes + 256;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -90,6 +97,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   const int num_n = (p.N + BN - 1) / BN;
   const int num_tiles = num_m * num_n;
   const int num_kb = (p.K + kBlockK - 1) / kBlockK;
+  const int split = p.split_k > 1 ? p.split_k : 1;
+  const int kpb = (num_kb + split - 1) / split;  // k-blocks per unit (host guarantees no empty slice)
+  const int num_units = num_tiles * split;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
@@ -116,9 +126,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     // ===================== TMA producer =====================
     if (lane == 0) {
       uint32_t it = 0;
-      uint32_t pf_it = 0;
-      int pf_tile = blockIdx.x, pf_kb = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x) {
+        const int tile = unit / split;
+        const int kb0 = (unit - tile * split) * kpb;
+        const int kb1 = min(num_kb, kb0 + kpb);
         // M tiles are visited starting from this rank's own row shard (m_rot), so an all-gather ⊕ GEMM
         // works on local rows while the peers' rows are still arriving over NVLink
         const int mt = ((tile % num_m) + p.m_rot) % num_m;
@@ -133,15 +144,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           }
           asm volatile("fence.proxy.async;" ::: "memory");
         }
-        for (int kb = 0; kb < num_kb; ++kb, ++it) {
-          // L2 prefetch cursor for the weight operand: runs `p.prefetch_kb` k-blocks ahead of the
-          // SMEM ring (across tile boundaries) so weight streaming is not limited by the per-SM
-          // number of outstanding DRAM misses of the ring itself.
-          while (pf_it < it + p.prefetch_kb && pf_tile < num_tiles) {
-            tma_prefetch_l2_2d(&tmap_b, pf_kb * kBlockK, (pf_tile / num_m) * BN);
-            ++pf_it;
-            if (++pf_kb == num_kb) { pf_kb = 0; pf_tile += gridDim.x; }
-          }
+        for (int kb = kb0; kb < kb1; ++kb, ++it) {
           const int s = it % S;
           const uint32_t ph = (it / S) & 1;
           mbar_wait(&empty_bar[s], ph ^ 1);
@@ -159,13 +162,15 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       constexpr uint32_t idesc = make_idesc_bf16(kBlockM, BN);
       uint32_t it = 0;
       uint32_t tcount = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tcount) {
+      for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x, ++tcount) {
+        const int kb0 = (unit % split) * kpb;
+        const int kb1 = min(num_kb, kb0 + kpb);
         const uint32_t buf = tcount & 1;
         const uint32_t aph = (tcount >> 1) & 1;
         mbar_wait(&tmem_empty[buf], aph ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + buf * BN;
-        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+        for (int kb = kb0; kb < kb1; ++kb, ++it) {
           const int s = it % S;
           const uint32_t ph = (it / S) & 1;
           mbar_wait(&full_bar[s], ph);
@@ -178,7 +183,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           for (int k = 0; k < kBlockK / kUmmaK; ++k) {
             // advance 32 B (16 bf16) along K inside the swizzle atom: +2 in 16-byte units
             umma_bf16<1>(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc,
-                         (kb > 0 || k > 0) ? 1u : 0u);
+                         (kb > kb0 || k > 0) ? 1u : 0u);
           }
           umma_commit(&empty_bar[s]);
         }
@@ -189,7 +194,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     // ===================== epilogue warps =====================
     const int q = warp & 3;  // TMEM lane quarter this warp may access
     uint32_t tcount = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tcount) {
+    for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x, ++tcount) {
+      const int tile = unit / split;
       const int m0 = (((tile % num_m) + p.m_rot) % num_m) * kBlockM;
       const int n0 = (tile / num_m) * BN;
       const uint32_t buf = tcount & 1;
@@ -219,74 +225,166 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         }
       }
 
-      if constexpr (EPI == kEpiStore) {
+      constexpr int OUT_W_ = (EPI == kEpiSiluMul) ? BN / 2 : BN;
+      // thread-private workspace layout: [unit][warp q][32-col chunk][j][lane] float4 — the reader of a value
+      // is the thread (q, lane) that wrote it, so every access is a fully coalesced 512-byte warp transaction
+      auto ws_ptr = [&](int u, int chunk, int j) {
+        return reinterpret_cast<float4*>(p.ws) +
+               ((((static_cast<size_t>(u) * 4 + q) * (BN / 32) + chunk) * 8 + j) * 32 + lane);
+      };
+      if (split > 1) {
 #pragma unroll 1
         for (int c = 0; c < BN; c += 32) {
           uint32_t v[32];
           tmem_ld_32x32(t_row + c, v);
           tmem_ld_wait();
-          if (row_ok) {
 #pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-              const int col = n0 + c + j;
-              if (col < out_N) {
-                float f[8];
+          for (int j = 0; j < 8; ++j)
+            *ws_ptr(unit, c / 32, j) = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
+                                                   __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tmem_empty[buf]);
+        // every k-slice CTA of this tile reduces and stores its own 1/split column share (reduce-scatter
+        // through L2): wait until all partners have published their partials. The partners are co-resident
+        // (persistent grid, one CTA per SM, grid % split == 0 keeps a tile's slices in the same round).
+        __threadfence();
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (warp == 2 && lane == 0) {
+          atomicAdd(p.tile_cnt + 2 * tile, 1u);
+          while (ld_acquire_gpu(p.tile_cnt + 2 * tile) < static_cast<uint32_t>(split)) {
+          }
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+      }
+      const int ks = unit - tile * split;
+      // output-column share of this unit (whole tile when split == 1)
+      const int share = OUT_W_ / split;
+      const int c_lo = ks * share, c_hi = c_lo + share;
+      // 32 (or 16) fp32 accumulator columns of this thread's row: from TMEM, or the slice-ordered sum of partials
+      auto load_acc = [&](int c, auto& v) {
+        constexpr int NC = sizeof(v) / sizeof(uint32_t);
+        if (split == 1) {
+          if constexpr (NC == 32) tmem_ld_32x32(t_row + c, v); else tmem_ld_32x16(t_row + c, v);
+          tmem_ld_wait();
+        } else {
+          float a[NC];
 #pragma unroll
-                for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[j + e]);
-                if (p.bias != nullptr) {
-                  uint4 bv = *reinterpret_cast<const uint4*>(p.bias + col);
-                  float2 b0 = unpack_bf16(bv.x), b1 = unpack_bf16(bv.y), b2 = unpack_bf16(bv.z),
-                         b3 = unpack_bf16(bv.w);
-                  f[0] += b0.x; f[1] += b0.y; f[2] += b1.x; f[3] += b1.y;
-                  f[4] += b2.x; f[5] += b2.y; f[6] += b3.x; f[7] += b3.y;
-                }
-                uint4 o;
-                o.x = pack_bf16(f[0], f[1]);
-                o.y = pack_bf16(f[2], f[3]);
-                o.z = pack_bf16(f[4], f[5]);
-                o.w = pack_bf16(f[6], f[7]);
-                st_v4(crow + col, o);
-              }
+          for (int e = 0; e < NC; ++e) a[e] = 0.f;
+          for (int sidx = 0; sidx < split; ++sidx) {
+#pragma unroll
+            for (int j = 0; j < NC / 4; ++j) {
+              const float4 x = __ldcg(ws_ptr(tile * split + sidx, c / 32, (c % 32) / 4 + j));
+              a[4 * j] += x.x; a[4 * j + 1] += x.y; a[4 * j + 2] += x.z; a[4 * j + 3] += x.w;
             }
           }
+#pragma unroll
+          for (int e = 0; e < NC; ++e) v[e] = __float_as_uint(a[e]);
+        }
+      };
+
+      // Output tiles go through a per-warp swizzled smem transpose so that every global (or peer / NVLink)
+      // store instruction writes full 128-byte row segments instead of 32 scattered 16-byte pieces.
+      constexpr int OUT_W = (EPI == kEpiSiluMul) ? BN / 2 : BN;   // output columns of this tile
+      constexpr int W = OUT_W < 64 ? OUT_W : 64;                  // columns per staged chunk
+      constexpr int LPR = W / 8;                                  // lanes (16 B each) per staged row
+      constexpr int RPI = 32 / LPR;                               // rows per store instruction
+      uint8_t* stg = epi_smem + (warp - 2) * 4096;
+      unsigned long long* rowptr = reinterpret_cast<unsigned long long*>(epi_smem + 16384) + (warp - 2) * 32;
+      rowptr[lane] = row_ok ? reinterpret_cast<unsigned long long>(crow) : 0ull;
+      __syncwarp();
+      auto stage_put = [&](int ch, const float* f) {  // 8 consecutive output columns of this lane's row
+        uint4 o;
+        o.x = pack_bf16(f[0], f[1]);
+        o.y = pack_bf16(f[2], f[3]);
+        o.z = pack_bf16(f[4], f[5]);
+        o.w = pack_bf16(f[6], f[7]);
+        *reinterpret_cast<uint4*>(stg + lane * (W * 2) + ((ch ^ (lane & (LPR - 1) & 7)) * 16)) = o;
+      };
+      auto stage_flush = [&](int col0, int col_end) {  // col0: first output column of the staged chunk
+        __syncwarp();
+#pragma unroll
+        for (int it = 0; it < 32 / RPI; ++it) {
+          const int r = it * RPI + lane / LPR;
+          const int ch = lane % LPR;
+          const uint4 o = *reinterpret_cast<const uint4*>(stg + r * (W * 2) + ((ch ^ (r & (LPR - 1) & 7)) * 16));
+          __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(rowptr[r]);
+          const int col = col0 + ch * 8;
+          if (dst != nullptr && col < out_N && col < col_end) st_v4(dst + col, o);
+        }
+        __syncwarp();
+      };
+
+      if constexpr (EPI == kEpiStore) {
+#pragma unroll 1
+        for (int c = c_lo; c < c_hi; c += W) {
+#pragma unroll
+          for (int h = 0; h < W; h += 32) {
+            if (c + h >= c_hi) break;
+            uint32_t v[32];
+            load_acc(c + h, v);
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              const int col = n0 + c + h + j;
+              float f[8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[j + e]);
+              if (p.bias != nullptr && col < out_N) {
+                uint4 bv = *reinterpret_cast<const uint4*>(p.bias + col);
+                float2 b0 = unpack_bf16(bv.x), b1 = unpack_bf16(bv.y), b2 = unpack_bf16(bv.z),
+                       b3 = unpack_bf16(bv.w);
+                f[0] += b0.x; f[1] += b0.y; f[2] += b1.x; f[3] += b1.y;
+                f[4] += b2.x; f[5] += b2.y; f[6] += b3.x; f[7] += b3.y;
+              }
+              stage_put((h + j) / 8, f);
+            }
+          }
+          stage_flush(n0 + c, n0 + c_hi);
         }
       } else {
         // SiLU-gate: tile columns [0, BN/2) hold gate, [BN/2, BN) hold up for the same
         // BN/2 output features (weights are interleaved per tile at load time).
         constexpr int H = BN / 2;
 #pragma unroll 1
-        for (int c = 0; c < H; c += 16) {
-          uint32_t g[16], u[16];
-          tmem_ld_32x16(t_row + c, g);
-          tmem_ld_32x16(t_row + H + c, u);
-          tmem_ld_wait();
-          if (row_ok) {
+        for (int c = c_lo; c < c_hi; c += W) {
+#pragma unroll
+          for (int h = 0; h < W; h += 16) {
+            if (c + h >= c_hi) break;
+            uint32_t g[16], u[16];
+            load_acc(c + h, g);
+            load_acc(H + c + h, u);
 #pragma unroll
             for (int j = 0; j < 16; j += 8) {
-              const int col = out_n0 + c + j;
-              if (col < out_N) {
-                float f[8];
+              float f[8];
 #pragma unroll
-                for (int e = 0; e < 8; ++e) {
-                  const float gv = __uint_as_float(g[j + e]);
-                  const float uv = __uint_as_float(u[j + e]);
-                  f[e] = gv / (1.0f + __expf(-gv)) * uv;
-                }
-                uint4 o;
-                o.x = pack_bf16(f[0], f[1]);
-                o.y = pack_bf16(f[2], f[3]);
-                o.z = pack_bf16(f[4], f[5]);
-                o.w = pack_bf16(f[6], f[7]);
-                st_v4(crow + col, o);
+              for (int e = 0; e < 8; ++e) {
+                const float gv = __uint_as_float(g[j + e]);
+                const float uv = __uint_as_float(u[j + e]);
+                f[e] = gv / (1.0f + __expf(-gv)) * uv;
               }
+              stage_put((h + j) / 8, f);
             }
+          }
+          stage_flush(out_n0 + c, out_n0 + c_hi);
+        }
+      }
+      // release the accumulator buffer back to the MMA warp (split-K released it after the partial write)
+      if (split == 1) {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tmem_empty[buf]);
+      } else {
+        // depart: the last slice to finish reading re-arms both counters for the next launch
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (warp == 2 && lane == 0) {
+          const uint32_t t = atomicAdd(p.tile_cnt + 2 * tile + 1, 1u);
+          if (t == static_cast<uint32_t>(split - 1)) {
+            p.tile_cnt[2 * tile] = 0u;
+            p.tile_cnt[2 * tile + 1] = 0u;
           }
         }
       }
-      // release the accumulator buffer back to the MMA warp
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty[buf]);
 
       if (p.rs_world > 0) {
         // GEMM ⊕ reduce-scatter: all four epilogue warps have stored their rows; publish the
@@ -298,7 +396,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           const int o0 = m0 / p.rows_per_rank;
           const int o1 = (m1 - 1) / p.rows_per_rank;
           for (int o = o0; o <= o1; ++o) {
-            red_add_release_sys(p.peer_cnt[o] + p.rs_rank, p.rs_inc);
+            red_add_relaxed_sys(p.peer_cnt[o] + p.rs_rank, p.rs_inc);
           }
         }
       }
@@ -326,8 +424,10 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmP
   }
   const int num_m = (p.M + kBlockM - 1) / kBlockM;
   const int num_n = (p.N + BN - 1) / BN;
-  const int tiles = num_m * num_n;
-  const int grid = tiles < num_sms() ? tiles : num_sms();
+  const int split = p.split_k > 1 ? p.split_k : 1;
+  const int tiles = num_m * num_n * split;
+  const int sms = (num_sms() / split) * split;  // split-K slices of a tile must run in the same round
+  const int grid = tiles < sms ? tiles : sms;
   kern<<<grid, kNumThreads, Cfg::kSmemBytes, stream>>>(ta, tb, p);
   CUDA_CHECK_RET(cudaGetLastError());
   return 0;
@@ -355,6 +455,42 @@ static int pick_bn(int M, int N, int epi, int forced) {
   return best;
 }
 
+// Decode-sized M: few output tiles, so tile shape and a K split are chosen together. Cost model in SM clocks,
+// calibrated on B200 (profiles/gemm_splitk.md): a 64-deep k-block costs ~650 clk for BN=256 and ~420 clk for
+// BN<=128 (SMEM fill bound: 16 KB of A per k-block regardless of BN), a split-K round adds ~2000 + 24*BN.
+static void pick_split(int M, int N, int K, int epi, int forced_bn, int64_t ws_bytes, int max_tiles, int* bn_out,
+                       int* split_out) {
+  const int sms = num_sms();
+  const int num_m = (M + kBlockM - 1) / kBlockM;
+  const int num_kb = (K + kBlockK - 1) / kBlockK;
+  double best = 1e30;
+  const int cands[4] = {256, 128, 64, 32};
+  for (int i = 0; i < 4; ++i) {
+    const int bn = cands[i];
+    if (forced_bn > 0 && bn != forced_bn) continue;
+    if (epi == kEpiSiluMul && bn < 64) continue;
+    const int tiles = num_m * ((N + bn - 1) / bn);
+    // measured per-k-block time in SM clocks (benchmarks/gemm_tune.py, profiles/gemm_splitk.md)
+    const double t_kb = bn >= 256 ? 650.0 : 420.0;
+    for (int split = 1; split <= 8; split *= 2) {
+      const int kpb = (num_kb + split - 1) / split;
+      const int out_w = epi == kEpiSiluMul ? bn / 2 : bn;
+      if (split > 1) {
+        if (kpb < 4 || (split - 1) * kpb >= num_kb) continue;            // no empty / tiny slices
+        if (out_w / split < (epi == kEpiSiluMul ? 16 : 32)) continue;     // column share granularity
+        if (static_cast<int64_t>(tiles) * split * kBlockM * bn * 4 > ws_bytes || tiles > max_tiles) continue;
+      }
+      const int units = tiles * split;
+      const int grid = (sms / split) * split;
+      const int waves = (units + grid - 1) / grid;
+      double unit_clk = kpb * t_kb + 700.0;
+      if (split > 1) unit_clk += 24.0 * bn + 2000.0;                      // partial write + rendezvous + share sum
+      const double cost = waves * unit_clk;
+      if (cost < best) { best = cost; *bn_out = bn; *split_out = split; }
+    }
+  }
+}
+
 }  // namespace b200
 
 using namespace b200;
@@ -372,33 +508,62 @@ struct GemmComm {
   uint32_t* peer_cnt[kMaxPeers];
 };
 
+static int g_max_split_m = -1, g_force_split = -1;
+
+// tuning aid (benchmarks/gemm_tune.py): force a split factor / the M ceiling of the split-K path at run time
+GLLM_EXPORT int gllm_gemm_tune(int force_split, int max_split_m) {
+  g_force_split = force_split;
+  g_max_split_m = max_split_m;
+  return 0;
+}
+
 GLLM_EXPORT int gllm_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, void* C,
                                int64_t ldc, int M, int N, int K, const void* bias, int epi,
-                               int force_bn, const GemmComm* comm, void* stream) {
+                               int force_bn, const GemmComm* comm, void* ws, int64_t ws_bytes, void* tile_cnt,
+                               int max_tiles, void* stream) {
   if (M <= 0 || N <= 0 || K <= 0) return 0;
   if ((K % 8) != 0 || (N % 8) != 0 || (lda % 8) != 0 || (ldw % 8) != 0 || (ldc % 8) != 0) {
     fprintf(stderr, "[gllm_b200] gemm_bf16: K, N and leading dims must be multiples of 8\n");
     return 1;
   }
-  const int bn = pick_bn(M, N, epi, force_bn);
+  int bn = pick_bn(M, N, epi, force_bn);
+  int split = 1;
+  {
+    int& max_split_m = g_max_split_m;
+    int& force_split = g_force_split;
+    if (max_split_m < 0) {
+      const char* e = getenv("GLLM_GEMM_SPLITK_MAX_M");
+      max_split_m = e ? atoi(e) : 512;
+    }
+    if (comm == nullptr && ws != nullptr && tile_cnt != nullptr && M <= max_split_m)
+      pick_split(M, N, K, epi, force_bn, ws_bytes, max_tiles, &bn, &split);
+    if (force_split < 0) {
+      const char* e = getenv("GLLM_GEMM_FORCE_SPLITK");  // tuning aid: only legal (bn, split) pairs
+      force_split = e ? atoi(e) : 0;
+    }
+    if (force_split > 0 && comm == nullptr && ws != nullptr) {
+      split = force_split;
+      const int num_kb = (K + kBlockK - 1) / kBlockK;
+      const int kpb = (num_kb + split - 1) / split;
+      const int out_w = epi == kEpiSiluMul ? bn / 2 : bn;
+      const int tiles = ((M + kBlockM - 1) / kBlockM) * ((N + bn - 1) / bn);
+      if ((split - 1) * kpb >= num_kb || out_w / split < (epi == kEpiSiluMul ? 16 : 32) || (split & (split - 1)) ||
+          static_cast<int64_t>(tiles) * split * kBlockM * bn * 4 > ws_bytes || tiles > max_tiles)
+        split = 1;
+    }
+  }
   CUtensorMap ta, tb;
   if (make_tmap_2d(&ta, A, M, K, lda * 2, kBlockM, kBlockK, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16)) return 1;
   if (make_tmap_2d(&tb, W, N, K, ldw * 2, bn, kBlockK, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16)) return 1;
   GemmParams p;
   memset(&p, 0, sizeof(p));
+  p.split_k = split;
+  p.ws = reinterpret_cast<float*>(ws);
+  p.tile_cnt = reinterpret_cast<uint32_t*>(tile_cnt);
   p.M = M; p.N = N; p.K = K;
   p.C = reinterpret_cast<__nv_bfloat16*>(C);
   p.ldc = static_cast<int>(ldc);
   p.bias = reinterpret_cast<const __nv_bfloat16*>(bias);
-  {
-    static int pf = -1;
-    if (pf < 0) {
-      const char* e = getenv("GLLM_GEMM_PREFETCH");
-      pf = e ? atoi(e) : 0;  // measured: no gain on B200 (profiles/gemm_bf16_v1.md)
-    }
-    // prefetching only pays when the weights are streamed once (few M tiles share them)
-    p.prefetch_kb = (M <= 1024) ? pf : 0;
-  }
   if (comm != nullptr) {
     p.a_ready = comm->a_ready;
     p.a_expected = comm->a_expected;

@@ -42,7 +42,8 @@ _FORCE_BN = int(os.environ.get("GLLM_GEMM_BN", "0"))
 _SMALLM_MAX = int(os.environ.get("GLLM_GEMM_SMALLM_MAX", "32"))   # M <= this -> swap-AB split-K kernel
 # (measured crossover vs the 128xBN kernel on B200: profiles/gemm_smallm.md)
 _FORCE_SPLIT = int(os.environ.get("GLLM_GEMM_SPLIT", "0"))
-_SMALLM_WS_FLOATS = 24 << 20
+_SMALLM_WS_FLOATS = 24 << 20   # fp32 partial-sum workspace shared by the swap-AB and the split-K kernels
+_SPLITK_MAX_TILES = 4096
 _smallm_ws = {}
 
 
@@ -50,7 +51,8 @@ def _smallm_workspace(device):
     ws = _smallm_ws.get(device)
     if ws is None:
         ws = (torch.empty(_SMALLM_WS_FLOATS, dtype=torch.float32, device=device),
-              torch.zeros(8192, dtype=torch.int32, device=device))
+              torch.zeros(8192, dtype=torch.int32, device=device),
+              torch.zeros(2 * _SPLITK_MAX_TILES, dtype=torch.int32, device=device))
         _smallm_ws[device] = ws
     return ws
 
@@ -58,7 +60,7 @@ def _smallm_workspace(device):
 def _linear_smallm(x, w, bias, out, silu: bool):
     m, k = x.shape
     n = w.shape[0]
-    ws, cnt = _smallm_workspace(x.device)
+    ws, cnt, _ = _smallm_workspace(x.device)
     L = _lib.load()
     rc = L.gllm_gemm_smallm(_p(x), x.stride(0), _p(w), w.stride(0), _p(out), out.stride(0), m, n, k, _p(bias),
                             1 if silu else 0, _FORCE_SPLIT, _p(ws), ws.numel(), _p(cnt), stream_ptr())
@@ -85,8 +87,10 @@ def linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None
     if comm is None and epi == 0 and _FORCE_BN == 0 and (m <= _SMALLM_MAX or (m <= 64 and k >= 8192)):
         return _linear_smallm(x, w, bias, out, False)
     L = _lib.load()
+    ws, _, tcnt = _smallm_workspace(x.device)
     rc = L.gllm_gemm_bf16(_p(x), x.stride(0), _p(w), w.stride(0), _p(out), out.stride(0), m, n, k, _p(bias),
-                          epi, _FORCE_BN, ctypes.byref(comm) if comm is not None else None, stream_ptr())
+                          epi, _FORCE_BN, ctypes.byref(comm) if comm is not None else None, _p(ws),
+                          ws.numel() * 4, _p(tcnt), _SPLITK_MAX_TILES, stream_ptr())
     check(rc, "gemm_bf16")
     _count()
     return out
@@ -107,9 +111,11 @@ def linear_silu_mul(x: torch.Tensor, w_interleaved: torch.Tensor, out: Optional[
     if m <= _SMALLM_MAX and _FORCE_BN == 0 and comm is None:
         return _linear_smallm(x, w_interleaved, None, out, True)
     L = _lib.load()
+    ws, _, tcnt = _smallm_workspace(x.device)
     rc = L.gllm_gemm_bf16(_p(x), x.stride(0), _p(w_interleaved), w_interleaved.stride(0), _p(out),
                           out.stride(0), m, n, k, None, 1, 256,
-                          ctypes.byref(comm) if comm is not None else None, stream_ptr())
+                          ctypes.byref(comm) if comm is not None else None, _p(ws), ws.numel() * 4, _p(tcnt),
+                          _SPLITK_MAX_TILES, stream_ptr())
     check(rc, "gemm_bf16(silu)")
     _count()
     return out

@@ -372,3 +372,35 @@ def test_gemm_fp8_block(m, n, k):
     q_r, s_r = ref.fp8_quant_group(x)
     assert torch.allclose(s.t(), s_r, rtol=1e-5)
     assert _rel_err(q.float(), q_r.float()) < 3e-2
+
+
+@pytest.mark.parametrize("m", [64, 128, 200, 256, 384, 512])
+@pytest.mark.parametrize("n,k", [(4096, 4096), (4096, 12288), (6144, 4096), (1000, 1536)])
+def test_gemm_splitk_decode_shapes(m, n, k):
+    """Decode-sized M takes the wide-tile split-K path (fp32 partials, last-arriver sum): exact shape sweep,
+    bias, and back-to-back launches (tile counters re-arm themselves)."""
+    from gllm_b200.ops import sm100
+    torch.manual_seed(m + n + k)
+    x = (torch.randn(m, k, device=_dev()) * 0.5).bfloat16()
+    w = (torch.randn(n, k, device=_dev()) * 0.05).bfloat16()
+    b = torch.randn(n, device=_dev()).bfloat16()
+    for bias in (None, b):
+        y = sm100.linear(x, w, bias)
+        yr = x.float() @ w.float().t() + (bias.float() if bias is not None else 0)
+        assert _rel_err(y, yr) < 6e-3, _rel_err(y, yr)
+    y2 = sm100.linear(x, w, None)
+    for _ in range(3):
+        assert torch.equal(y2, sm100.linear(x, w, None))   # deterministic slice-ordered reduction
+
+
+@pytest.mark.parametrize("m", [64, 256, 384])
+def test_gemm_splitk_silu(m):
+    from gllm_b200.ops import sm100
+    torch.manual_seed(m)
+    i, k = 12288, 4096
+    x = (torch.randn(m, k, device=_dev()) * 0.5).bfloat16()
+    w = (torch.randn(2 * i, k, device=_dev()) * 0.02).bfloat16()
+    y = sm100.linear_silu_mul(x, ref.interleave_gate_up(w, 128))
+    h = x.float() @ w.float().t()
+    yr = torch.nn.functional.silu(h[:, :i]) * h[:, i:]
+    assert _rel_err(y, yr) < 1e-2

@@ -510,6 +510,36 @@ struct GemmComm {
 
 static int g_max_split_m = -1, g_force_split = -1;
 
+// (tile width, split-K factor) for a plain / all-gather-gated / reduce-scatter GEMM. Deterministic in its
+// arguments: the consumer of a GEMM ⊕ reduce-scatter calls it again (gllm_gemm_bf16_tiles_covering) to know
+// how many unit arrivals to expect.
+static void choose_cfg(int M, int N, int K, int epi, int force_bn, int64_t ws_bytes, int max_tiles, int* bn_out,
+                       int* split_out) {
+  int bn = pick_bn(M, N, epi, force_bn);
+  int split = 1;
+  if (g_max_split_m < 0) {
+    const char* e = getenv("GLLM_GEMM_SPLITK_MAX_M");
+    g_max_split_m = e ? atoi(e) : 512;
+  }
+  if (g_force_split < 0) {
+    const char* e = getenv("GLLM_GEMM_FORCE_SPLITK");  // tuning aid: only legal (bn, split) pairs
+    g_force_split = e ? atoi(e) : 0;
+  }
+  if (ws_bytes > 0 && M <= g_max_split_m) pick_split(M, N, K, epi, force_bn, ws_bytes, max_tiles, &bn, &split);
+  if (g_force_split > 0 && ws_bytes > 0) {
+    split = g_force_split;
+    const int num_kb = (K + kBlockK - 1) / kBlockK;
+    const int kpb = (num_kb + split - 1) / split;
+    const int out_w = epi == kEpiSiluMul ? bn / 2 : bn;
+    const int tiles = ((M + kBlockM - 1) / kBlockM) * ((N + bn - 1) / bn);
+    if ((split - 1) * kpb >= num_kb || out_w / split < (epi == kEpiSiluMul ? 16 : 32) || (split & (split - 1)) ||
+        static_cast<int64_t>(tiles) * split * kBlockM * bn * 4 > ws_bytes || tiles > max_tiles)
+      split = 1;
+  }
+  *bn_out = bn;
+  *split_out = split;
+}
+
 // tuning aid (benchmarks/gemm_tune.py): force a split factor / the M ceiling of the split-K path at run time
 GLLM_EXPORT int gllm_gemm_tune(int force_split, int max_split_m) {
   g_force_split = force_split;
@@ -526,32 +556,8 @@ GLLM_EXPORT int gllm_gemm_bf16(const void* A, int64_t lda, const void* W, int64_
     fprintf(stderr, "[gllm_b200] gemm_bf16: K, N and leading dims must be multiples of 8\n");
     return 1;
   }
-  int bn = pick_bn(M, N, epi, force_bn);
-  int split = 1;
-  {
-    int& max_split_m = g_max_split_m;
-    int& force_split = g_force_split;
-    if (max_split_m < 0) {
-      const char* e = getenv("GLLM_GEMM_SPLITK_MAX_M");
-      max_split_m = e ? atoi(e) : 512;
-    }
-    if (comm == nullptr && ws != nullptr && tile_cnt != nullptr && M <= max_split_m)
-      pick_split(M, N, K, epi, force_bn, ws_bytes, max_tiles, &bn, &split);
-    if (force_split < 0) {
-      const char* e = getenv("GLLM_GEMM_FORCE_SPLITK");  // tuning aid: only legal (bn, split) pairs
-      force_split = e ? atoi(e) : 0;
-    }
-    if (force_split > 0 && comm == nullptr && ws != nullptr) {
-      split = force_split;
-      const int num_kb = (K + kBlockK - 1) / kBlockK;
-      const int kpb = (num_kb + split - 1) / split;
-      const int out_w = epi == kEpiSiluMul ? bn / 2 : bn;
-      const int tiles = ((M + kBlockM - 1) / kBlockM) * ((N + bn - 1) / bn);
-      if ((split - 1) * kpb >= num_kb || out_w / split < (epi == kEpiSiluMul ? 16 : 32) || (split & (split - 1)) ||
-          static_cast<int64_t>(tiles) * split * kBlockM * bn * 4 > ws_bytes || tiles > max_tiles)
-        split = 1;
-    }
-  }
+  int bn = 128, split = 1;
+  choose_cfg(M, N, K, epi, force_bn, ws != nullptr && tile_cnt != nullptr ? ws_bytes : 0, max_tiles, &bn, &split);
   CUtensorMap ta, tb;
   if (make_tmap_2d(&ta, A, M, K, lda * 2, kBlockM, kBlockK, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16)) return 1;
   if (make_tmap_2d(&tb, W, N, K, ldw * 2, bn, kBlockK, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16)) return 1;
@@ -597,14 +603,15 @@ GLLM_EXPORT int gllm_gemm_bf16(const void* A, int64_t lda, const void* W, int64_
 
 // Number of (m_tile, n_tile) pairs whose rows intersect [row0, row1) — used by the consumer
 // of a fused GEMM ⊕ reduce-scatter to know how many tile arrivals to expect per source rank.
-GLLM_EXPORT int gllm_gemm_bf16_tiles_covering(int M, int N, int epi, int force_bn, int row0,
-                                              int row1) {
+GLLM_EXPORT int gllm_gemm_bf16_tiles_covering(int M, int N, int K, int epi, int force_bn, int row0, int row1,
+                                              int64_t ws_bytes, int max_tiles) {
   if (row1 > M) row1 = M;
   if (row1 <= row0) return 0;
-  const int bn = pick_bn(M, N, epi, force_bn);
+  int bn = 128, split = 1;
+  choose_cfg(M, N, K, epi, force_bn, ws_bytes, max_tiles, &bn, &split);
   const int t0 = row0 / kBlockM;
   const int t1 = (row1 - 1) / kBlockM;
-  return (t1 - t0 + 1) * ((N + bn - 1) / bn);
+  return (t1 - t0 + 1) * ((N + bn - 1) / bn) * split;  // every k-slice unit publishes its column share
 }
 
 // Grouped (MoE) GEMM: rows of A are expert-sorted and padded to 128-row tiles; tile t uses the weight

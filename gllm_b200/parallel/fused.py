@@ -245,7 +245,10 @@ class FusedTPComm(TPComm):
         dummy = self.blob[self.off_stage[parity]: self.off_stage[parity] + 16].view(torch.bfloat16)
         sm100.linear(x, w, bias if self.tp_rank == 0 else None, out=_FakeOut(t, n, dummy), comm=c)
         r0 = self.tp_rank * self.rpr
-        n_tiles = self.L.gllm_gemm_bf16_tiles_covering(t, n, 0, sm100._FORCE_BN, r0, min(r0 + self.rpr, t))
+        ws = sm100._smallm_workspace(x.device)[0]
+        n_tiles = self.L.gllm_gemm_bf16_tiles_covering(t, n, x.shape[1], 0, sm100._FORCE_BN, r0,
+                                                       min(r0 + self.rpr, t), ws.numel() * 4,
+                                                       sm100._SPLITK_MAX_TILES)
         return self._reduce_norm(parity, n_tiles, None, residual is not None, norm_w, eps)
 
     def reduce_add_norm(self, partial, residual, norm_w, eps):

@@ -142,7 +142,7 @@ def main():
     runner = llm.worker.runner
 
     def one_pass():
-        llm.generate(tokens=prompts, output_lens=out_lens, ignore_eos=True, top_k=1, temperature=0.0)
+        return llm.generate(tokens=prompts, output_lens=out_lens, ignore_eos=True, top_k=1, temperature=0.0)
 
     def barrier():
         if world > 1:
@@ -175,8 +175,9 @@ def main():
     # ---- region B: end to end through the public API, wall clock ----
     barrier()
     t0 = time.perf_counter()
+    seqs = None
     for _ in range(args.steps):
-        one_pass()
+        seqs = one_pass()
     barrier()
     wall_s = time.perf_counter() - t0
     if sampler:
@@ -196,6 +197,17 @@ def main():
         except Exception:  # noqa: BLE001
             pass
         eng_steps = stats1["steps"] - stats0["steps"]
+        # request latencies of the last end-to-end pass (all requests arrive together at t0: offline workload)
+        lat = None
+        try:
+            ttft = sorted((q.first_token_time - q.arrival_time) * 1e3 for q in seqs if q.first_token_time)
+            tpot = sorted((q.finish_time - q.first_token_time) * 1e3 / max(q.num_output_tokens - 1, 1)
+                          for q in seqs if q.first_token_time and q.finish_time and q.num_output_tokens > 1)
+            lat = {"p50_ttft_ms": round(ttft[len(ttft) // 2], 1), "p99_ttft_ms": round(ttft[int(len(ttft) * 0.99)], 1),
+                   "p50_tpot_ms": round(tpot[len(tpot) // 2], 2), "p99_tpot_ms": round(tpot[int(len(tpot) * 0.99)], 2),
+                   "arrival": "all requests at t0 (offline batch)"}
+        except Exception:  # noqa: BLE001
+            pass
         out = {
             "metric": "output tokens/sec, offline throughput (benchmark_throughput workload), Qwen3-8B TP",
             "value": round(value, 1), "unit": "tokens/s", "n_gpus": args.gpus, "steps": args.steps,
@@ -218,6 +230,7 @@ def main():
                     "h2d_bytes_per_step": (stats1["h2d_bytes"] - stats0["h2d_bytes"]) // max(args.steps, 1),
                     "d2h_bytes_per_step": (stats1["d2h_bytes"] - stats0["d2h_bytes"]) // max(args.steps, 1)},
             "gpu_launches": int(launches),
+            "latency": lat,
         }
         print(json.dumps(out), flush=True)
     if world > 1 and dist.is_initialized():

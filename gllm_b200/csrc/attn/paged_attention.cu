@@ -129,6 +129,8 @@ attn_decode_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_cons
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + SM::kStages * SM::kStageBytes);
   uint64_t* empty_bar = full_bar + SM::kStages;
 
+  griddep_launch();
+  griddep_wait();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int groups_per_kv = p.G / p.GP;
   const int kvh = blockIdx.x / groups_per_kv;
@@ -329,6 +331,8 @@ attn_decode_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_cons
 // out[seq, head, :] = sum_s softmax_s(lse) * part_o[seq, head, s, :]
 __global__ void attn_merge_kernel(const float* __restrict__ part_o, const float* __restrict__ part_lse,
                                   __nv_bfloat16* __restrict__ out, int num_splits, int D) {
+  griddep_launch();
+  griddep_wait();
   const size_t sh = blockIdx.x;  // seq * Hq + head
   float m = -INFINITY;
   for (int s = 0; s < num_splits; ++s) m = fmaxf(m, part_lse[sh * num_splits + s]);
@@ -588,8 +592,7 @@ static int launch_decode(const CUtensorMap& tk, const CUtensorMap& tv, const Att
     configured = true;
   }
   dim3 grid(p.Hkv * (p.G / p.GP), num_seqs, p.num_splits);
-  attn_decode_kernel<D><<<grid, kAttnThreads, SM::kBytes, st>>>(tk, tv, p);
-  CUDA_CHECK_RET(cudaGetLastError());
+  CUDA_CHECK_RET(launch_pdl(attn_decode_kernel<D>, grid, dim3(kAttnThreads), SM::kBytes, st, tk, tv, p));
   return 0;
 }
 
@@ -654,9 +657,9 @@ GLLM_EXPORT int gllm_attn_decode(const void* q, int64_t q_ts, void* out, const v
   if (p.num_splits > 1) {
     // merge covers sequences [seq_offset, seq_offset + num_seqs)
     const size_t off = (size_t)seq_offset * Hq;
-    attn_merge_kernel<<<num_seqs * Hq, D < 128 ? D : 128, 0, st>>>(
-        p.part_o + off * p.num_splits * D, p.part_lse + off * p.num_splits, p.out + off * D, p.num_splits, D);
-    CUDA_CHECK_RET(cudaGetLastError());
+    CUDA_CHECK_RET(launch_pdl(attn_merge_kernel, dim3(num_seqs * Hq), dim3(D < 128 ? D : 128), 0, st,
+                              p.part_o + off * p.num_splits * D, p.part_lse + off * p.num_splits,
+                              p.out + off * D, p.num_splits, D));
   }
   return 0;
 }

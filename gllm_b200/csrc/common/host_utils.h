@@ -69,6 +69,34 @@ inline int make_tmap_2d(CUtensorMap* map, const void* base, uint64_t rows, uint6
   return 0;
 }
 
+// Programmatic dependent launch: the kernel may start (prologue, weight prefetch) while its predecessor in the
+// stream is still draining; it must execute `griddep_wait()` (ptx.cuh) before touching anything the
+// predecessor wrote. Only kernels written that way are launched through this helper. GLLM_PDL=0 disables it.
+inline bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("GLLM_PDL");
+    v = (e == nullptr || atoi(e) != 0) ? 1 : 0;
+  }
+  return v == 1;
+}
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                              Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 inline int num_sms() {
   static int n = 0;
   if (n == 0) {

@@ -345,6 +345,10 @@ __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
 __device__ __forceinline__ void red_add_release_sys(uint32_t* p, uint32_t v) {
   asm volatile("red.release.sys.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
+// programmatic dependent launch (host side: host_utils.h launch_pdl). Both are no-ops for a normal launch.
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void griddep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // relaxed system-scope signals: issue ONE __threadfence_system() first, then any number of these (a
 // `*.release.sys` per peer costs one MEMBAR.ALL.SYS each — profiles/sass_summary.md)
 __device__ __forceinline__ void red_add_relaxed_sys(uint32_t* p, uint32_t v) {

@@ -32,6 +32,8 @@ __global__ void rmsnorm_kernel(const __nv_bfloat16* __restrict__ x, const __nv_b
                                const __nv_bfloat16* __restrict__ w, __nv_bfloat16* out,
                                __nv_bfloat16* residual_out, int H, int64_t ldx, float eps) {
   __shared__ float red[32];
+  griddep_launch();  // let the next kernel (usually a GEMM) start its prologue + weight prefetch now
+  griddep_wait();    // ... while this one waits for its own producer to finish
   const int row = blockIdx.x;
   const int nvec = H >> 3;
   const __nv_bfloat16* xr = x + static_cast<size_t>(row) * ldx;
@@ -150,9 +152,9 @@ GLLM_EXPORT int gllm_rmsnorm(const void* x, const void* residual, const void* w,
   auto RO = reinterpret_cast<__nv_bfloat16*>(residual_out);
 #define LAUNCH(NV_)                                                                              \
   if (R != nullptr)                                                                              \
-    rmsnorm_kernel<NV_, true><<<T, threads, 0, st>>>(X, R, W, O, RO, H, ldx, eps);               \
+    CUDA_CHECK_RET(launch_pdl(rmsnorm_kernel<NV_, true>, dim3(T), dim3(threads), 0, st, X, R, W, O, RO, H, ldx, eps)); \
   else                                                                                           \
-    rmsnorm_kernel<NV_, false><<<T, threads, 0, st>>>(X, R, W, O, RO, H, ldx, eps);
+    CUDA_CHECK_RET(launch_pdl(rmsnorm_kernel<NV_, false>, dim3(T), dim3(threads), 0, st, X, R, W, O, RO, H, ldx, eps));
   if (nv == 1) { LAUNCH(1) }
   else if (nv == 2) { LAUNCH(2) }
   else if (nv == 4) { LAUNCH(4) }

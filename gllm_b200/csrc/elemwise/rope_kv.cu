@@ -43,6 +43,8 @@ __device__ __forceinline__ int mrope_axis(int i, int sec0, int sec1) {
 
 template <int C>  // elements per lane, D = 32 * C
 __global__ void rope_kv_kernel(const RopeParams p) {
+  griddep_launch();
+  griddep_wait();
   const int t = blockIdx.x;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   const int D = 32 * C;
@@ -59,7 +61,9 @@ __global__ void rope_kv_kernel(const RopeParams p) {
   }
   const int slot = p.slots != nullptr ? p.slots[t] : -1;
 
-  for (int hh = warp; hh < n_heads; hh += nwarps) {
+  // one head per warp: blockIdx.y strides the head list so a decode batch still fills the machine and no
+  // warp walks several heads serially (the per-head chain of dependent global loads is the whole cost)
+  for (int hh = blockIdx.y * nwarps + warp; hh < n_heads; hh += nwarps * gridDim.y) {
     const bool is_q = hh < p.Hq;
     const bool is_k = !is_q && hh < p.Hq + p.Hkv;
     const int h = is_q ? hh : (is_k ? hh - p.Hq : hh - p.Hq - p.Hkv);
@@ -177,13 +181,14 @@ GLLM_EXPORT int gllm_rope_kv_write(void* q, int64_t q_ts, int64_t q_hs, int Hq, 
     return 1;
   }
   const int n_heads = Hq + 2 * Hkv;
-  int warps = n_heads < 8 ? n_heads : 8;
+  int warps = n_heads < 4 ? n_heads : 4;
   if (warps < 1) warps = 1;
+  const dim3 grid(T, (n_heads + warps - 1) / warps);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   switch (C) {
-    case 2: rope_kv_kernel<2><<<T, warps * 32, 0, st>>>(p); break;
-    case 4: rope_kv_kernel<4><<<T, warps * 32, 0, st>>>(p); break;
-    case 8: rope_kv_kernel<8><<<T, warps * 32, 0, st>>>(p); break;
+    case 2: CUDA_CHECK_RET(launch_pdl(rope_kv_kernel<2>, grid, dim3(warps * 32), 0, st, p)); break;
+    case 4: CUDA_CHECK_RET(launch_pdl(rope_kv_kernel<4>, grid, dim3(warps * 32), 0, st, p)); break;
+    case 8: CUDA_CHECK_RET(launch_pdl(rope_kv_kernel<8>, grid, dim3(warps * 32), 0, st, p)); break;
     default:
       fprintf(stderr, "[gllm_b200] rope_kv_write: unsupported head_dim %d\n", D);
       return 1;

@@ -92,6 +92,13 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
+  // Programmatic dependent launch: dependents may start their prologue now; we ourselves may already be running
+  // while the previous kernel drains. Grouped (MoE) mode reads device-side tile metadata right away, so it
+  // waits here; the dense path first puts weight tiles in flight (producer warp below) and waits afterwards.
+  griddep_launch();
+  const bool grouped = p.tile_expert != nullptr || p.num_m_tiles_ptr != nullptr;
+  if (grouped) griddep_wait();
+
   const int num_m = p.num_m_tiles_ptr != nullptr ? min(*p.num_m_tiles_ptr, (p.M + kBlockM - 1) / kBlockM)
                                                  : (p.M + kBlockM - 1) / kBlockM;
   const int num_n = (p.N + BN - 1) / BN;
@@ -126,6 +133,23 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     // ===================== TMA producer =====================
     if (lane == 0) {
       uint32_t it = 0;
+      // weights (B) do not depend on the previous kernel: put the first stages' B tiles in flight, then wait
+      uint32_t pre = 0;
+      if (!grouped) {
+        if (static_cast<int>(blockIdx.x) < num_units) {
+          const int tile = blockIdx.x / split;
+          const int kb0 = (blockIdx.x - tile * split) * kpb;
+          const int kb1 = min(num_kb, kb0 + kpb);
+          const int n0 = (tile / num_m) * BN;
+          pre = static_cast<uint32_t>(min(S, kb1 - kb0));
+          for (uint32_t i = 0; i < pre; ++i) {
+            uint8_t* sb = smem + i * Cfg::kStageBytes + Cfg::kABytes;
+            mbar_expect_tx(&full_bar[i], Cfg::kStageBytes);
+            tma_load_2d(sb, &tmap_b, &full_bar[i], (kb0 + static_cast<int>(i)) * kBlockK, n0, kEvictNormal);
+          }
+        }
+        griddep_wait();
+      }
       for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x) {
         const int tile = unit / split;
         const int kb0 = (unit - tile * split) * kpb;
@@ -147,9 +171,13 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         for (int kb = kb0; kb < kb1; ++kb, ++it) {
           const int s = it % S;
           const uint32_t ph = (it / S) & 1;
-          mbar_wait(&empty_bar[s], ph ^ 1);
           uint8_t* sa = smem + s * Cfg::kStageBytes;
           uint8_t* sb = sa + Cfg::kABytes;
+          if (it < pre) {  // B tile of this stage is already in flight (issued before griddep_wait)
+            tma_load_2d(sa, &tmap_a, &full_bar[s], kb * kBlockK, m0, kEvictNormal);
+            continue;
+          }
+          mbar_wait(&empty_bar[s], ph ^ 1);
           mbar_expect_tx(&full_bar[s], Cfg::kStageBytes);
           tma_load_2d(sa, &tmap_a, &full_bar[s], kb * kBlockK, m0, kEvictNormal);
           tma_load_2d(sb, &tmap_b, &full_bar[s], kb * kBlockK, n0 + b_row_off, kEvictNormal);
@@ -192,6 +220,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     }
   } else {
     // ===================== epilogue warps =====================
+    if (!grouped) griddep_wait();
     const int q = warp & 3;  // TMEM lane quarter this warp may access
     uint32_t tcount = 0;
     for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x, ++tcount) {
@@ -428,8 +457,7 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmP
   const int tiles = num_m * num_n * split;
   const int sms = (num_sms() / split) * split;  // split-K slices of a tile must run in the same round
   const int grid = tiles < sms ? tiles : sms;
-  kern<<<grid, kNumThreads, Cfg::kSmemBytes, stream>>>(ta, tb, p);
-  CUDA_CHECK_RET(cudaGetLastError());
+  CUDA_CHECK_RET(launch_pdl(kern, dim3(grid), dim3(kNumThreads), Cfg::kSmemBytes, stream, ta, tb, p));
   return 0;
 }
 

@@ -79,9 +79,24 @@ gemm_smallm_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_cons
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
 
+  griddep_launch();
   if (warp == 0) {
     if (lane == 0) {
       uint32_t it = 0;
+      // PDL: weight tiles of the first stages go in flight before waiting for the previous kernel
+      uint32_t pre = 0;
+      if (static_cast<int>(blockIdx.x) < num_units) {
+        const int nt = blockIdx.x / p.S, sp = blockIdx.x % p.S;
+        const int kb0 = sp * p.kb_per_split;
+        const int kb1 = min(kb0 + p.kb_per_split, num_kb);
+        pre = static_cast<uint32_t>(min(S, kb1 - kb0));
+        for (uint32_t i = 0; i < pre; ++i) {
+          mbar_expect_tx(&full_bar[i], stage_bytes);
+          tma_load_2d(smem + i * stage_bytes, &tmap_w, &full_bar[i], (kb0 + static_cast<int>(i)) * kBK, nt * kWTile,
+                      kEvictFirst);
+        }
+      }
+      griddep_wait();
       for (int u = blockIdx.x; u < num_units; u += gridDim.x) {
         const int nt = u / p.S, sp = u % p.S;
         const int kb0 = sp * p.kb_per_split;
@@ -89,9 +104,13 @@ gemm_smallm_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_cons
         for (int kb = kb0; kb < kb1; ++kb, ++it) {
           const int s = it % S;
           const uint32_t ph = (it / S) & 1;
-          mbar_wait(&empty_bar[s], ph ^ 1);
           uint8_t* sw = smem + s * stage_bytes;
           uint8_t* sx = sw + w_bytes;
+          if (it < pre) {
+            tma_load_2d(sx, &tmap_x, &full_bar[s], kb * kBK, 0, kEvictLast);
+            continue;
+          }
+          mbar_wait(&empty_bar[s], ph ^ 1);
           mbar_expect_tx(&full_bar[s], stage_bytes);
           tma_load_2d(sw, &tmap_w, &full_bar[s], kb * kBK, nt * kWTile, kEvictFirst);
           tma_load_2d(sx, &tmap_x, &full_bar[s], kb * kBK, 0, kEvictLast);
@@ -342,7 +361,7 @@ GLLM_EXPORT int gllm_gemm_smallm(const void* A, int64_t lda, const void* W, int6
   }
   const int units = num_n * p.S;
   const int grid = units < sms ? units : sms;
-  gemm_smallm_kernel<<<grid, kSmThreads, smem_bytes, reinterpret_cast<cudaStream_t>(stream)>>>(tw, tx, p);
-  CUDA_CHECK_RET(cudaGetLastError());
+  CUDA_CHECK_RET(launch_pdl(gemm_smallm_kernel, dim3(grid), dim3(kSmThreads), smem_bytes,
+                            reinterpret_cast<cudaStream_t>(stream), tw, tx, p));
   return 0;
 }

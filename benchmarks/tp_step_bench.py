@@ -25,7 +25,7 @@ def main():
                            model_max_length=2064)
         r = ModelRunner(cfg)
         r.init(f"cuda:{local}")
-        for b, ctx, pre in ((16, 512, 0), (128, 512, 0), (256, 512, 0), (4, 0, 1024)):
+        for b, ctx, pre in ((16, 512, 0), (64, 512, 0), (128, 512, 0), (256, 512, 0), (4, 0, 1024)):
             batch = make_batch(b, ctx, pre, cfg.page_size)
             for _ in range(3):
                 r.step(batch)

@@ -29,7 +29,8 @@ struct TpState {
   uint32_t rs_expected[2][kMaxTp];  // per parity, per source rank: tile arrivals consumed so far
   uint32_t ag_epoch[3];             // per gather buffer: number of pushes so far (diagnostic)
   uint32_t ticket[4];               // grid tickets
-  uint32_t pad[9];                  // -> ag_expected starts at byte 128
+  uint32_t ll_epoch;                // one-shot LL all-reduce: calls completed so far (flag value of the next call - 1)
+  uint32_t pad[8];                  // -> ag_expected starts at byte 128
   // per gather buffer, per 128-row block: rows that must have arrived before the block may be read.
   // Arrival counters (symmetric `flags`) are bumped once per pushed row by the row's owner, so a
   // consumer GEMM can start on the blocks that are complete while the rest is still in flight.
@@ -54,6 +55,13 @@ struct ReduceNormParams {
   int tp, rank, rows_per_rank, rows_valid, H;
   float eps;
   int T;  // total tokens of this forward (all ranks)
+  int bcast;  // one-shot all-reduce mode: every rank holds and reduces ALL T rows (rows_per_rank == T)
+  // bcast + push_x: the kernel first publishes this rank's partial row to every rank's staging slot (one-shot
+  // all-reduce ⊕ add ⊕ RMSNorm in ONE kernel for decode-sized T)
+  const __nv_bfloat16* push_x;
+  int64_t push_ld;
+  __nv_bfloat16* stage_peers[kMaxTp];
+  uint32_t* cnt_peers[kMaxTp];
 };
 
 template <int NV>
@@ -63,6 +71,23 @@ __global__ void rs_reduce_norm_kernel(const ReduceNormParams p) {
   const int row = blockIdx.x;  // local row in this rank's shard
   const int nvec = p.H >> 3;
 
+  if (p.push_x != nullptr) {
+    if (row < p.rows_valid) {
+      const __nv_bfloat16* src = p.push_x + static_cast<size_t>(row) * p.push_ld;
+      for (int i = threadIdx.x * 8; i < p.H; i += blockDim.x * 8) {
+        const uint4 v = *reinterpret_cast<const uint4*>(src + i);
+        for (int d = 0; d < p.tp; ++d) {
+          const int peer = (p.rank + d) % p.tp;
+          st_v4(p.stage_peers[peer] + (static_cast<size_t>(p.rank) * p.rows_per_rank + row) * p.H + i, v);
+        }
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && row < p.rows_valid) {
+      __threadfence_system();
+      for (int d = 0; d < p.tp; ++d) red_add_relaxed_sys(p.cnt_peers[(p.rank + d) % p.tp] + p.rank, 1u);
+    }
+  }
   if (p.local_x == nullptr && threadIdx.x < p.tp) {
     const int src = threadIdx.x;
     const uint32_t target = p.st->rs_expected[p.parity][src] + p.n_tiles[src];
@@ -83,7 +108,7 @@ __global__ void rs_reduce_norm_kernel(const ReduceNormParams p) {
         float a[8] = {0, 0, 0, 0, 0, 0, 0, 0};
         if (p.local_x != nullptr) {
           const uint4 t = *reinterpret_cast<const uint4*>(
-              p.local_x + (static_cast<size_t>(p.rank) * p.rows_per_rank + row) * p.local_ld + i * 8);
+              p.local_x + (p.bcast ? static_cast<size_t>(row) : static_cast<size_t>(p.rank) * p.rows_per_rank + row) * p.local_ld + i * 8);
           const float2 f0 = unpack_bf16(t.x), f1 = unpack_bf16(t.y), f2 = unpack_bf16(t.z), f3 = unpack_bf16(t.w);
           a[0] = f0.x; a[1] = f0.y; a[2] = f1.x; a[3] = f1.y; a[4] = f2.x; a[5] = f2.y; a[6] = f3.x; a[7] = f3.y;
         } else {
@@ -135,7 +160,8 @@ __global__ void rs_reduce_norm_kernel(const ReduceNormParams p) {
   }
   if (row < p.rows_valid && p.norm_w != nullptr) {
     const float inv = rsqrtf(ss / static_cast<float>(p.H) + p.eps);
-    const size_t grow = static_cast<size_t>(p.rank) * p.rows_per_rank + row;
+    const size_t grow = p.bcast ? static_cast<size_t>(row) : static_cast<size_t>(p.rank) * p.rows_per_rank + row;
+    const int n_push = p.bcast ? 1 : p.tp;  // bcast: the result stays local (every rank computes all rows)
 #pragma unroll
     for (int j = 0; j < NV; ++j) {
       const int i = threadIdx.x + j * blockDim.x;
@@ -148,7 +174,7 @@ __global__ void rs_reduce_norm_kernel(const ReduceNormParams p) {
         o.z = pack_bf16(v[j][4] * inv * w2.x, v[j][5] * inv * w2.y);
         o.w = pack_bf16(v[j][6] * inv * w3.x, v[j][7] * inv * w3.y);
         // all-gather by producer-side stores: own copy first, then the peers (rank-rotated order)
-        for (int d = 0; d < p.tp; ++d) {
+        for (int d = 0; d < n_push; ++d) {
           const int peer = (p.rank + d) % p.tp;
           st_v4(p.ag_peers[peer] + grow * p.H + i * 8, o);
         }
@@ -161,8 +187,8 @@ __global__ void rs_reduce_norm_kernel(const ReduceNormParams p) {
   if (threadIdx.x == 0) {
     if (row < p.rows_valid && p.norm_w != nullptr) {
       __threadfence_system();
-      const int blk = (p.rank * p.rows_per_rank + row) / kFlagBlockRows;
-      for (int d = 0; d < p.tp; ++d) {
+      const int blk = (p.bcast ? row : p.rank * p.rows_per_rank + row) / kFlagBlockRows;
+      for (int d = 0; d < (p.bcast ? 1 : p.tp); ++d) {
         const int peer = (p.rank + d) % p.tp;
         red_add_relaxed_sys(p.flag_peers[peer] + blk, 1u);
       }
@@ -184,6 +210,134 @@ __global__ void rs_reduce_norm_kernel(const ReduceNormParams p) {
     for (int b = threadIdx.x; b < nblk; b += blockDim.x) {
       const int rows = min(p.T, (b + 1) * kFlagBlockRows) - b * kFlagBlockRows;
       p.st->ag_expected[p.ag_idx][b] += static_cast<uint32_t>(rows);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// One-shot all-reduce ⊕ residual add ⊕ RMSNorm for decode-sized T, low-latency ("LL") protocol: every 4 bytes
+// of payload travel in an 8-byte store together with the call's epoch, so the receiver needs no fence, no
+// counter and no second round trip — it polls the slot until the epoch matches. One CTA per token row; sums
+// are taken in rank order (deterministic). Slots are double-buffered by call parity (a peer is at most one
+// call ahead). Replaces NCCL all_reduce + fused_add_rms_norm (reference: gllm/layers/linear.py:247-250).
+// ---------------------------------------------------------------------------------------------
+struct LLParams {
+  const __nv_bfloat16* x;      // this rank's partial [T, H]
+  int64_t ldx;
+  __nv_bfloat16* residual;     // [T, H] replicated running residual (in/out)
+  int residual_in;
+  const __nv_bfloat16* norm_w;
+  __nv_bfloat16* out;          // [T, H] normed output (local)
+  uint2* ll_peers[kMaxTp];     // LL slot base of this parity on every rank: [src][row_cap][H/2] x 8 bytes
+  TpState* st;
+  int tp, rank, T, H, row_cap;
+  float eps;
+};
+
+__device__ __forceinline__ void st_volatile_v2(uint2* p, uint32_t a, uint32_t b) {
+  asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(a), "r"(b) : "memory");
+}
+__device__ __forceinline__ uint2 ld_volatile_v2(const uint2* p) {
+  uint2 v;
+  asm volatile("ld.volatile.global.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p) : "memory");
+  return v;
+}
+
+__global__ void ll_allreduce_norm_kernel(const LLParams p) {
+  __shared__ float red[32];
+  __shared__ uint32_t s_last;
+  griddep_launch();  // the consumer GEMM may start streaming its weights while we exchange partials
+  griddep_wait();
+  const int row = blockIdx.x;
+  const int tid = threadIdx.x;
+  const bool active = tid * 8 < p.H;
+  const uint32_t epoch = *reinterpret_cast<const volatile uint32_t*>(&p.st->ll_epoch) + 1u;
+  const size_t slot0 = static_cast<size_t>(row) * (p.H / 2) + tid * 4;
+  const size_t src_stride = static_cast<size_t>(p.row_cap) * (p.H / 2);
+  uint32_t mine[4] = {0, 0, 0, 0};
+  if (active) {
+    const uint4 v = *reinterpret_cast<const uint4*>(p.x + static_cast<size_t>(row) * p.ldx + tid * 8);
+    mine[0] = v.x; mine[1] = v.y; mine[2] = v.z; mine[3] = v.w;
+    for (int d = 1; d < p.tp; ++d) {
+      uint2* dst = p.ll_peers[(p.rank + d) % p.tp] + p.rank * src_stride + slot0;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) st_volatile_v2(dst + k, mine[k], epoch);
+    }
+  }
+  float a[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (active) {
+    const uint2* mybuf = p.ll_peers[p.rank];
+    for (int s = 0; s < p.tp; ++s) {
+      uint32_t w[4];
+      if (s == p.rank) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) w[k] = mine[k];
+      } else {
+        const uint2* src = mybuf + s * src_stride + slot0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          uint2 v;
+          do { v = ld_volatile_v2(src + k); } while (v.y != epoch);
+          w[k] = v.x;
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float2 f = unpack_bf16(w[k]);
+        a[2 * k] += f.x; a[2 * k + 1] += f.y;
+      }
+    }
+  }
+  float ss = 0.f;
+  if (active) {
+    __nv_bfloat16* rp = p.residual + static_cast<size_t>(row) * p.H + tid * 8;
+    if (p.residual_in) {
+      const uint4 r = *reinterpret_cast<const uint4*>(rp);
+      const float2 r0 = unpack_bf16(r.x), r1 = unpack_bf16(r.y), r2 = unpack_bf16(r.z), r3 = unpack_bf16(r.w);
+      // the all-reduced value is rounded to bf16 before the add, like the unfused reference
+      a[0] = __bfloat162float(__float2bfloat16(a[0])) + r0.x; a[1] = __bfloat162float(__float2bfloat16(a[1])) + r0.y;
+      a[2] = __bfloat162float(__float2bfloat16(a[2])) + r1.x; a[3] = __bfloat162float(__float2bfloat16(a[3])) + r1.y;
+      a[4] = __bfloat162float(__float2bfloat16(a[4])) + r2.x; a[5] = __bfloat162float(__float2bfloat16(a[5])) + r2.y;
+      a[6] = __bfloat162float(__float2bfloat16(a[6])) + r3.x; a[7] = __bfloat162float(__float2bfloat16(a[7])) + r3.y;
+    }
+    uint4 o;
+    o.x = pack_bf16(a[0], a[1]); o.y = pack_bf16(a[2], a[3]); o.z = pack_bf16(a[4], a[5]); o.w = pack_bf16(a[6], a[7]);
+    *reinterpret_cast<uint4*>(rp) = o;
+    const float2 q0 = unpack_bf16(o.x), q1 = unpack_bf16(o.y), q2 = unpack_bf16(o.z), q3 = unpack_bf16(o.w);
+    a[0] = q0.x; a[1] = q0.y; a[2] = q1.x; a[3] = q1.y; a[4] = q2.x; a[5] = q2.y; a[6] = q3.x; a[7] = q3.y;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) ss += a[e] * a[e];
+  }
+  {
+    const int lane = tid & 31, warp = tid >> 5;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    if (lane == 0) red[warp] = ss;
+    __syncthreads();
+    float t = lane < ((blockDim.x + 31) >> 5) ? red[lane] : 0.f;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    ss = t;
+  }
+  if (active) {
+    const float inv = rsqrtf(ss / static_cast<float>(p.H) + p.eps);
+    const uint4 wv = *reinterpret_cast<const uint4*>(p.norm_w + tid * 8);
+    const float2 w0 = unpack_bf16(wv.x), w1 = unpack_bf16(wv.y), w2 = unpack_bf16(wv.z), w3 = unpack_bf16(wv.w);
+    uint4 o;
+    o.x = pack_bf16(a[0] * inv * w0.x, a[1] * inv * w0.y);
+    o.y = pack_bf16(a[2] * inv * w1.x, a[3] * inv * w1.y);
+    o.z = pack_bf16(a[4] * inv * w2.x, a[5] * inv * w2.y);
+    o.w = pack_bf16(a[6] * inv * w3.x, a[7] * inv * w3.y);
+    *reinterpret_cast<uint4*>(p.out + static_cast<size_t>(row) * p.H + tid * 8) = o;
+  }
+  // the last CTA to finish closes the epoch (all CTAs are co-resident: T <= row_cap <= 64)
+  __syncthreads();
+  if (tid == 0) {
+    const uint32_t old = atomicAdd(&p.st->ticket[1], 1u);
+    s_last = (old == gridDim.x - 1) ? 1u : 0u;
+    if (s_last) {
+      p.st->ticket[1] = 0u;
+      p.st->ll_epoch = epoch;
     }
   }
 }
@@ -237,6 +391,11 @@ struct ReduceNormArgs {
   int parity, ag_idx, tp, rank, rows_per_rank, rows_valid, H;
   float eps;
   int T;
+  int bcast;
+  const void* push_x;
+  int64_t push_ld;
+  void* stage_peers[kMaxTp];
+  void* cnt_peers[kMaxTp];
 };
 
 GLLM_EXPORT int gllm_rs_reduce_norm(const ReduceNormArgs* a, void* stream) {
@@ -258,6 +417,13 @@ GLLM_EXPORT int gllm_rs_reduce_norm(const ReduceNormArgs* a, void* stream) {
   p.parity = a->parity; p.ag_idx = a->ag_idx; p.tp = a->tp; p.rank = a->rank;
   p.rows_per_rank = a->rows_per_rank; p.rows_valid = a->rows_valid; p.H = a->H; p.eps = a->eps;
   p.T = a->T;
+  p.bcast = a->bcast;
+  p.push_x = reinterpret_cast<const __nv_bfloat16*>(a->push_x);
+  p.push_ld = a->push_ld;
+  for (int i = 0; i < kMaxTp; ++i) {
+    p.stage_peers[i] = reinterpret_cast<__nv_bfloat16*>(a->stage_peers[i]);
+    p.cnt_peers[i] = reinterpret_cast<uint32_t*>(a->cnt_peers[i]);
+  }
   if ((p.T + kFlagBlockRows - 1) / kFlagBlockRows > kMaxBlocks) return 1;
   if (p.H % 8 != 0 || p.tp > kMaxTp) return 1;
   const int nvec = p.H / 8;
@@ -267,6 +433,8 @@ GLLM_EXPORT int gllm_rs_reduce_norm(const ReduceNormArgs* a, void* stream) {
   // one CTA per shard row; at least one CTA so the bookkeeping/flags advance even for empty shards
   const int grid = p.rows_per_rank > 0 ? p.rows_per_rank : 1;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  // (plain launch: measured slower with programmatic dependent launch — the gated consumer GEMM then polls
+  // system-scope flags next to the reduction, profiles/tp_fused.md)
   if (nv == 1) rs_reduce_norm_kernel<1><<<grid, threads, 0, st>>>(p);
   else if (nv == 2) rs_reduce_norm_kernel<2><<<grid, threads, 0, st>>>(p);
   else if (nv == 4) rs_reduce_norm_kernel<4><<<grid, threads, 0, st>>>(p);
@@ -291,6 +459,38 @@ GLLM_EXPORT int gllm_wait_ag_flags(const void* flags, const void* st, int ag_idx
   wait_ag_flags_kernel<<<1, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       reinterpret_cast<const uint32_t*>(flags), reinterpret_cast<const TpState*>(st), ag_idx, nblk);
   CUDA_CHECK_RET(cudaGetLastError());
+  return 0;
+}
+
+struct LLArgs {
+  const void* x;
+  int64_t ldx;
+  void* residual;
+  int residual_in;
+  const void* norm_w;
+  void* out;
+  void* ll_peers[kMaxTp];
+  void* st;
+  int tp, rank, T, H, row_cap;
+  float eps;
+};
+
+GLLM_EXPORT int gllm_ll_allreduce_norm(const LLArgs* a, void* stream) {
+  if (a->T <= 0) return 0;
+  if (a->H % 8 != 0 || a->H / 8 > 1024 || a->T > a->row_cap || a->tp > kMaxTp) return 1;
+  LLParams p;
+  p.x = reinterpret_cast<const __nv_bfloat16*>(a->x);
+  p.ldx = a->ldx;
+  p.residual = reinterpret_cast<__nv_bfloat16*>(a->residual);
+  p.residual_in = a->residual_in;
+  p.norm_w = reinterpret_cast<const __nv_bfloat16*>(a->norm_w);
+  p.out = reinterpret_cast<__nv_bfloat16*>(a->out);
+  for (int i = 0; i < kMaxTp; ++i) p.ll_peers[i] = reinterpret_cast<uint2*>(a->ll_peers[i]);
+  p.st = reinterpret_cast<TpState*>(a->st);
+  p.tp = a->tp; p.rank = a->rank; p.T = a->T; p.H = a->H; p.row_cap = a->row_cap; p.eps = a->eps;
+  const int threads = ((a->H / 8 + 31) / 32) * 32;
+  CUDA_CHECK_RET(launch_pdl(ll_allreduce_norm_kernel, dim3(a->T), dim3(threads), 0,
+                            reinterpret_cast<cudaStream_t>(stream), p));
   return 0;
 }
 

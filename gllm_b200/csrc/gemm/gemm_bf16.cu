@@ -44,6 +44,9 @@ struct GemmParams {
   uint32_t rs_inc;
   __nv_bfloat16* peer_out[kMaxPeers];
   uint32_t* peer_cnt[kMaxPeers];
+  // rs_bcast: every row goes to EVERY rank's staging slot (one-shot all-reduce for decode-sized T: each rank
+  // then reduces all rows itself, comm/tp_fused.cu bcast mode) instead of only to the row's owner
+  int rs_bcast;
   // grouped (MoE) mode: M tile t multiplies the weight slab of expert tile_expert[t]
   const int32_t* tile_expert;
   const int32_t* num_m_tiles_ptr;  // device scalar: number of live M tiles
@@ -245,7 +248,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         row_ok = crow != nullptr;
       } else if (row_ok) {
         if (p.rs_world > 0) {
-          const int owner = row / p.rows_per_rank;
+          const int owner = p.rs_bcast ? 0 : row / p.rows_per_rank;
           const int r_local = row - owner * p.rows_per_rank;
           crow = p.peer_out[owner] +
                  (static_cast<size_t>(p.rs_rank) * p.rows_per_rank + r_local) * p.ldc;
@@ -340,7 +343,14 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           const uint4 o = *reinterpret_cast<const uint4*>(stg + r * (W * 2) + ((ch ^ (r & (LPR - 1) & 7)) * 16));
           __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(rowptr[r]);
           const int col = col0 + ch * 8;
-          if (dst != nullptr && col < out_N && col < col_end) st_v4(dst + col, o);
+          if (dst != nullptr && col < out_N && col < col_end) {
+            if (p.rs_bcast) {
+              const ptrdiff_t delta = (dst - p.peer_out[0]) + col;
+              for (int pr = 0; pr < p.rs_world; ++pr) st_v4(p.peer_out[pr] + delta, o);
+            } else {
+              st_v4(dst + col, o);
+            }
+          }
         }
         __syncwarp();
       };
@@ -422,8 +432,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         if (warp == 2 && lane == 0) {
           __threadfence_system();
           const int m1 = min(m0 + kBlockM, p.M);
-          const int o0 = m0 / p.rows_per_rank;
-          const int o1 = (m1 - 1) / p.rows_per_rank;
+          const int o0 = p.rs_bcast ? 0 : m0 / p.rows_per_rank;
+          const int o1 = p.rs_bcast ? p.rs_world - 1 : (m1 - 1) / p.rows_per_rank;
           for (int o = o0; o <= o1; ++o) {
             red_add_relaxed_sys(p.peer_cnt[o] + p.rs_rank, p.rs_inc);
           }
@@ -534,6 +544,7 @@ struct GemmComm {
   uint32_t rs_inc;
   void* peer_out[kMaxPeers];
   uint32_t* peer_cnt[kMaxPeers];
+  int rs_bcast;
 };
 
 static int g_max_split_m = -1, g_force_split = -1;
@@ -605,6 +616,7 @@ GLLM_EXPORT int gllm_gemm_bf16(const void* A, int64_t lda, const void* W, int64_
     p.rs_world = comm->rs_world;
     p.rs_rank = comm->rs_rank;
     p.rows_per_rank = comm->rows_per_rank;
+    p.rs_bcast = comm->rs_bcast;
     p.rs_inc = comm->rs_inc;
     for (int i = 0; i < kMaxPeers; ++i) {
       p.peer_out[i] = reinterpret_cast<__nv_bfloat16*>(comm->peer_out[i]);

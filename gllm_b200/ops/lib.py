@@ -38,6 +38,7 @@ class GemmComm(ctypes.Structure):
         ("rs_inc", c_uint32),
         ("peer_out", c_void_p * MAX_PEERS),
         ("peer_cnt", c_void_p * MAX_PEERS),
+        ("rs_bcast", c_int),
     ]
 
 

@@ -17,6 +17,7 @@ Reference behaviour replaced: GEMM -> NCCL all_reduce -> fused_add_rms_norm on r
 from __future__ import annotations
 
 import ctypes
+import os
 from ctypes import c_float, c_int, c_int64, c_uint32, c_void_p
 from typing import Optional
 
@@ -38,7 +39,16 @@ class ReduceNormArgs(ctypes.Structure):
         ("ag_peers", c_void_p * MAX_PEERS), ("flag_peers", c_void_p * MAX_PEERS), ("unnormed_out", c_void_p),
         ("st", c_void_p), ("parity", c_int), ("ag_idx", c_int), ("tp", c_int), ("rank", c_int),
         ("rows_per_rank", c_int), ("rows_valid", c_int), ("H", c_int), ("eps", c_float), ("T", c_int),
+        ("bcast", c_int), ("push_x", c_void_p), ("push_ld", c_int64), ("stage_peers", c_void_p * MAX_PEERS),
+        ("cnt_peers", c_void_p * MAX_PEERS),
     ]
+
+
+class LLArgs(ctypes.Structure):
+    """Mirror of `LLArgs` in csrc/comm/tp_fused.cu (one-shot LL all-reduce + add + RMSNorm)."""
+    _fields_ = [("x", c_void_p), ("ldx", c_int64), ("residual", c_void_p), ("residual_in", c_int),
+                ("norm_w", c_void_p), ("out", c_void_p), ("ll_peers", c_void_p * MAX_PEERS), ("st", c_void_p),
+                ("tp", c_int), ("rank", c_int), ("T", c_int), ("H", c_int), ("row_cap", c_int), ("eps", c_float)]
 
 
 class EpArgs(ctypes.Structure):
@@ -49,6 +59,7 @@ class EpArgs(ctypes.Structure):
                 ("H", c_int), ("r_max", c_int)]
 
 
+_ONESHOT = os.environ.get("GLLM_TP_ONESHOT", "1") != "0"
 MAX_BLOCKS = 256   # kMaxBlocks in csrc/comm/tp_fused.cu (128-row blocks per gather buffer)
 SMALL_T = 64       # forwards with <= this many tokens use the NCCL strategy (see begin_forward)
 
@@ -62,6 +73,8 @@ def _declare(L):
     L.gllm_wait_ag_flags.restype = c_int
     L.gllm_tp_state_bytes.argtypes = []
     L.gllm_tp_state_bytes.restype = c_int
+    L.gllm_ll_allreduce_norm.argtypes = [ctypes.POINTER(LLArgs), c_void_p]
+    L.gllm_ll_allreduce_norm.restype = c_int
     L.gllm_ep_state_bytes.argtypes = []
     L.gllm_ep_state_bytes.restype = c_int
     L.gllm_ep_dispatch.argtypes = [ctypes.POINTER(EpArgs), c_void_p, c_int64, c_void_p, c_int, c_void_p]
@@ -101,6 +114,10 @@ class FusedTPComm(TPComm):
         total = base_sync + 128 + 4 * MAX_BLOCKS * 3
         assert t_pad <= 128 * MAX_BLOCKS
         total = (total + 255) // 256 * 256
+        # LL slots of the one-shot all-reduce: [parity][src][SMALL_T rows][H/2] x 8 bytes
+        ll_bytes = tp * SMALL_T * hidden_size * 4
+        self.off_ll = [total, total + ll_bytes]
+        total += 2 * ll_bytes
         self.blob = symm.empty(total, dtype=torch.uint8, device=self.device)
         self.blob.zero_()
         self.hdl = symm.rendezvous(self.blob, self.group.group_name)
@@ -126,6 +143,7 @@ class FusedTPComm(TPComm):
         self.rs_call = 0
         self.ag_call = 0
         self.small = False
+        self.oneshot = False
         self.cur_ag = None  # (ag_idx, tensor view) produced by the last reduce_norm
         self.ep = None      # expert-parallel all-to-all buffers, created by the first MoE block
         self.ep_call = 0
@@ -138,6 +156,9 @@ class FusedTPComm(TPComm):
         # all-reduce beat the sharded dataflow there (measured on 2xB200: 4.6 ms vs 7.0 ms per step at
         # batch 16), so such forwards run the baseline strategy; everything else runs fused.
         self.small = num_tokens <= SMALL_T
+        # decode-sized forwards: one-shot all-reduce fused into the GEMM epilogue + reduce/add/norm kernel
+        # (every rank pushes its partial rows to every rank); needs T rows per source in the staging slots
+        self.oneshot = self.small and _ONESHOT and num_tokens <= self.rpr_max
         self.T = num_tokens
         self.rpr = (num_tokens + self.tp_size - 1) // self.tp_size
         self.rs_call = 0
@@ -156,7 +177,10 @@ class FusedTPComm(TPComm):
         off = self.off_ag[idx]
         return self.blob[off: off + self.T * self.H * 2].view(torch.bfloat16).view(self.T, self.H)
 
-    def _reduce_norm(self, parity: int, n_tiles, local_x, residual_in: bool, norm_w, eps: float):
+    def _reduce_norm(self, parity: int, n_tiles, local_x, residual_in: bool, norm_w, eps: float,
+                     bcast: bool = False, push_x=None):
+        """bcast=True: one-shot all-reduce form — every rank received every rank's partial for ALL T rows and
+        reduces them itself; the normed rows stay local (no gather push) and the residual is replicated."""
         ag_idx = self._next_ag_idx()
         a = ReduceNormArgs()
         a.stage = self.local_base + self.off_stage[parity]
@@ -176,10 +200,22 @@ class FusedTPComm(TPComm):
         a.parity, a.ag_idx, a.tp, a.rank = parity, ag_idx, self.tp_size, self.tp_rank
         a.rows_per_rank, a.rows_valid, a.H, a.eps = self.rpr, self._rows_valid(), self.H, float(eps)
         a.T = self.T
+        a.bcast = 1 if bcast else 0
+        if bcast:
+            a.rows_per_rank = a.rows_valid = self.T
+        if push_x is not None:
+            assert bcast and push_x.stride(1) == 1
+            a.push_x, a.push_ld = push_x.data_ptr(), push_x.stride(0)
+            for p in range(self.tp_size):
+                a.stage_peers[p] = self.peer_base[p] + self.off_stage[parity]
+                a.cnt_peers[p] = self.peer_base[p] + self.off_cnt[parity]
         check(self.L.gllm_rs_reduce_norm(ctypes.byref(a), stream_ptr()), "rs_reduce_norm")
         from gllm_b200.ops import sm100
         sm100._count()
         h = self._ag_view(ag_idx)
+        if bcast:
+            self.cur_ag = None  # all rows were written by this rank's own kernel: nothing to gate on
+            return h, self.residual_buf[: self.T]
         self.cur_ag = (ag_idx, h)
         return h, self.residual_buf[: self.rpr]
 
@@ -200,6 +236,8 @@ class FusedTPComm(TPComm):
     def first_norm(self, x: torch.Tensor, norm_w: torch.Tensor, eps: float):
         """Embedding output (replicated) -> (normed gather buffer, residual shard)."""
         if self.small:
+            if self.oneshot:
+                return self._reduce_norm(0, 0, x, False, norm_w, eps, bcast=True)
             return super().first_norm(x, norm_w, eps)
         return self._reduce_norm(0, 0, x, False, norm_w, eps)
 
@@ -230,31 +268,57 @@ class FusedTPComm(TPComm):
     def row_linear_add_norm(self, x, w, residual, norm_w, eps, bias=None):
         from gllm_b200.ops import sm100
         if self.small:
+            # decode-sized T: best local GEMM for the shape (swap-AB / split-K), then the one-kernel
+            # all-reduce ⊕ add ⊕ norm (reduce_add_norm below); TPComm.row_linear_add_norm does exactly that
             return super().row_linear_add_norm(x, w, residual, norm_w, eps, bias)
         parity = self.rs_call % 2
         self.rs_call += 1
         t, n = x.shape[0], w.shape[0]
         assert t == self.T and n == self.H
+        bcast = self.small
         c = GemmComm()
         c.a_ready = None
-        c.rs_world, c.rs_rank, c.rows_per_rank, c.rs_inc = self.tp_size, self.tp_rank, self.rpr, 1
+        c.rs_world, c.rs_rank, c.rows_per_rank, c.rs_inc = self.tp_size, self.tp_rank, (t if bcast else self.rpr), 1
+        c.rs_bcast = 1 if bcast else 0
         for p in range(self.tp_size):
             c.peer_out[p] = self.peer_base[p] + self.off_stage[parity]
             c.peer_cnt[p] = self.peer_base[p] + self.off_cnt[parity]
         # the epilogue writes into the peers' staging slots; `out` is only a shape carrier
         dummy = self.blob[self.off_stage[parity]: self.off_stage[parity] + 16].view(torch.bfloat16)
         sm100.linear(x, w, bias if self.tp_rank == 0 else None, out=_FakeOut(t, n, dummy), comm=c)
-        r0 = self.tp_rank * self.rpr
+        r0 = 0 if bcast else self.tp_rank * self.rpr
         ws = sm100._smallm_workspace(x.device)[0]
         n_tiles = self.L.gllm_gemm_bf16_tiles_covering(t, n, x.shape[1], 0, sm100._FORCE_BN, r0,
-                                                       min(r0 + self.rpr, t), ws.numel() * 4,
+                                                       t if bcast else min(r0 + self.rpr, t), ws.numel() * 4,
                                                        sm100._SPLITK_MAX_TILES)
-        return self._reduce_norm(parity, n_tiles, None, residual is not None, norm_w, eps)
+        return self._reduce_norm(parity, n_tiles, None, residual is not None, norm_w, eps, bcast=bcast)
 
     def reduce_add_norm(self, partial, residual, norm_w, eps):
         from gllm_b200.ops import sm100
         if self.small:
-            return super().reduce_add_norm(partial, residual, norm_w, eps)
+            if not self.oneshot or partial.dtype != torch.bfloat16:
+                return super().reduce_add_norm(partial, residual, norm_w, eps)
+            # one-shot all-reduce: push the partial rows to every rank, sum all tp partials locally, + residual,
+            # RMSNorm — one kernel instead of NCCL all-reduce + add/norm
+            parity = self.rs_call % 2
+            self.rs_call += 1
+            assert partial.shape[0] == self.T and partial.shape[1] == self.H and partial.stride(1) == 1
+            if self.H // 8 > 1024:   # rows wider than one CTA: counter-based one-shot form
+                return self._reduce_norm(parity, self.T, None, residual is not None, norm_w, eps, bcast=True,
+                                         push_x=partial)
+            h = self._ag_view(self._next_ag_idx())
+            a = LLArgs()
+            a.x, a.ldx = partial.data_ptr(), partial.stride(0)
+            a.residual, a.residual_in = self.residual_buf.data_ptr(), 1 if residual is not None else 0
+            a.norm_w, a.out = norm_w.data_ptr(), h.data_ptr()
+            for p in range(self.tp_size):
+                a.ll_peers[p] = self.peer_base[p] + self.off_ll[parity]
+            a.st = self.state.data_ptr()
+            a.tp, a.rank, a.T, a.H, a.row_cap, a.eps = self.tp_size, self.tp_rank, self.T, self.H, SMALL_T, float(eps)
+            check(self.L.gllm_ll_allreduce_norm(ctypes.byref(a), stream_ptr()), "ll_allreduce_norm")
+            sm100._count()
+            self.cur_ag = None
+            return h, self.residual_buf[: self.T]
         parity = self.rs_call % 2
         self.rs_call += 1
         assert partial.shape[0] == self.T and partial.shape[1] == self.H and partial.stride(1) == 1

@@ -251,10 +251,29 @@ class Worker(ProfilerMixin):
             pass
 
 
+async def _run_worker_async(worker: Worker):
+    """`--use-async-worker`: the same role loop as a coroutine that yields to the event loop between engine
+    iterations, so control-plane coroutines (profiler control, health probes) can interleave
+    (reference: gllm/async_worker.py:6-63)."""
+    import asyncio
+    idle = 0
+    while not worker.stop:
+        if worker.step():
+            idle = 0
+            await asyncio.sleep(0)
+        else:
+            idle += 1
+            await asyncio.sleep(0.0002 if idle > 2000 else 0)
+
+
 def run_worker(worker: Worker):
     """Entry point of a spawned worker process (reference: gllm/worker.py:252-265)."""
     try:
         worker.init()
+        if getattr(worker.cfg, "use_async_worker", False):
+            import asyncio
+            asyncio.run(_run_worker_async(worker))
+            return
         idle = 0
         while not worker.stop:
             if worker.step():

@@ -21,7 +21,8 @@ def _free_port():
     return p
 
 
-def test_spawn_mode_pp2_generates():
+@pytest.mark.parametrize("async_worker", [False, True])
+def test_spawn_mode_pp2_generates(async_worker):
     code = f"""
 import sys
 sys.path.insert(0, {ROOT!r})
@@ -30,7 +31,7 @@ if __name__ == "__main__":
     from gllm_b200.models.presets import tiny
     llm = LLM(tiny("Qwen3ForCausalLM", num_hidden_layers=4), load_format="dummy", pp_size=2, tp_size=1, maxp=48,
               maxd=16, num_cpu_pages=128, model_max_length=256, log_stats=False, device="cpu",
-              master_port={_free_port()}, schedule_method="token_throttling")
+              master_port={_free_port()}, schedule_method="token_throttling", use_async_worker={async_worker})
     outs = llm.generate(tokens=[[5, 17, 99], [9] * 40, list(range(20, 120))], output_lens=[6, 7, 8], ignore_eos=True)
     assert [len(s.token_ids) - s.prompt_len for s in outs] == [6, 7, 8]
     print("SPAWN_OK")

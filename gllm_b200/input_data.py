@@ -78,7 +78,14 @@ class BatchArrays:
 
 
 def _page_array(seq) -> np.ndarray:
-    return np.asarray(seq.page_table, dtype=np.int32)
+    """numpy view of the page table; converting the Python list every step costs O(pages) per sequence, so the
+    mirror is rebuilt only when the table changed length (every `page_size` tokens) or was reset."""
+    pt = seq.pt_np
+    n = len(seq.page_table)
+    if pt is None or pt.shape[0] != n or (n and (pt[0] != seq.page_table[0] or pt[-1] != seq.page_table[-1])):
+        pt = np.asarray(seq.page_table, dtype=np.int32)
+        seq.pt_np = pt
+    return pt
 
 
 def build_batch(entries, page_size: int, vocab_size: int, batch_id: int = 0, mrope: bool = False) -> BatchArrays:
@@ -197,6 +204,8 @@ class InputData:
         self._top_p = buf((max_seqs,), f32)
         self._rep_penalty = buf((max_seqs,), f32)
         self._state_slot = buf((max_seqs,), i32)
+        self._tok_seq = buf((max_tokens,), i32)
+        self.need_tok_seq = False  # MLA attention wants token -> sequence for mixed / prefill batches
         self.batch: Optional[BatchArrays] = None
         self.num_tokens = self.num_seqs = self.num_decode_seqs = self.num_emit = 0
         self.max_q_len = self.max_seq_len = 0
@@ -233,6 +242,9 @@ class InputData:
         else:
             self._put(self._positions, batch.positions if batch.positions.ndim == 1 else batch.positions[0])
         self._put(self._slots, batch.slot_mapping)
+        if self.need_tok_seq and not batch.is_decode_only():
+            qsl = batch.query_start_loc
+            self._put(self._tok_seq, np.repeat(np.arange(batch.num_seqs, dtype=np.int32), np.diff(qsl)))
         self._put(self._block_table, batch.block_table)
         self._put(self._seq_lens, batch.seq_lens)
         self._put(self._qsl, batch.query_start_loc)
@@ -280,6 +292,13 @@ class InputData:
 
     @property
     def slot_mapping(self): return self._slots[1][: self._n_tok()]
+
+    @property
+    def tok_seq(self):
+        """token -> sequence row, or None when every sequence has exactly one token (decode)."""
+        if self.padded_tokens or self.num_decode_seqs == self.num_seqs:
+            return None
+        return self._tok_seq[1][: self.num_tokens]
 
     @property
     def block_table(self): return self._block_table[1][: self._n_seq()]

@@ -71,6 +71,7 @@ class MemoryManager:
         for page in seq.page_table:
             self.free_page(page)
         seq.page_table = []
+        seq.pt_np = None
         seq.page_hashes = []
 
     def get_num_free_pages(self) -> int:

@@ -99,6 +99,7 @@ class ModelRunner:
         mrope = self.model.rope.mrope_section is not None if hasattr(self.model, "rope") else False
         self.input_data = InputData(self.max_num_batched_tokens, max(self.max_running_seqs, 1), max_blocks,
                                     self.device, mrope=mrope)
+        self.input_data.need_tok_seq = bool(self.loader.use_mla)
         h, dt = self.spec.hidden_size, self.spec.dtype
         if not ps.is_first_pp_rank():
             self.input_hidden = torch.zeros(self.max_num_batched_tokens, h, dtype=dt, device=self.device)

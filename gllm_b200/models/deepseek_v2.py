@@ -75,15 +75,17 @@ class MLAAttention(nn.Module):
         q = q.view(t, hl, self.qk_dim)
         kv_a = Fn.linear(h, self.kv_a_w)
         kv_c, _ = Fn.rmsnorm(kv_a[:, : self.kv_lora].contiguous(), self.kv_a_norm_w, self.eps)
-        k_pe = kv_a[:, self.kv_lora:].contiguous().view(t, 1, self.rope_dim)
-        q_pe = q[:, :, self.nope:].contiguous()
         if kv_cache is None:
             return q[:, :, : self.v_dim].reshape(t, hl * self.v_dim).contiguous()
+        cache = kv_cache.k_cache[self.layer_id]
+        if h.is_cuda and self.kv_lora == 512 and self.rope_dim == 64:
+            return self._forward_absorbed(inp, q, kv_c, kv_a[:, self.kv_lora:], cache)
+        k_pe = kv_a[:, self.kv_lora:].contiguous().view(t, 1, self.rope_dim)
+        q_pe = q[:, :, self.nope:].contiguous()
         # GPT-J style (interleaved) rotary on the rope dims only; oracle op (strided sub-views)
         ref.rope_kv_write(q_pe, k_pe, None, inp.positions, self.rope.cos_sin, self.rope_dim, False, None, None,
                           self.eps, None, None, None)
         latent = torch.cat([kv_c, k_pe.view(t, self.rope_dim)], dim=-1).view(t, 1, self.head_dim)
-        cache = kv_cache.k_cache[self.layer_id]
         ref.write_kv_cache(latent, None, cache, None, inp.slot_mapping)
         q = torch.cat([q[:, :, : self.nope], q_pe], dim=-1)
         out = torch.empty(t, hl, self.v_dim, dtype=h.dtype, device=h.device)
@@ -104,6 +106,35 @@ class MLAAttention(nn.Module):
             att = att.masked_fill((kj > qi).unsqueeze(0), float("-inf"))
             out[q0:q1] = torch.einsum("hqk,khd->qhd", torch.softmax(att, -1), v.float()).to(h.dtype)
         return out.view(t, hl * self.v_dim)
+
+    def _absorbed_weights(self):
+        """W_UK [hl, nope, 512] and W_UV [hl, 512, v] views of kv_b_proj, made contiguous once
+        (reference: MLAAttention.process_weights, gllm/layers/attention.py:106-127)."""
+        w = getattr(self, "_w_abs", None)
+        if w is None or w[2] != self.kv_b_w.data_ptr():
+            kvb = self.kv_b_w.data.view(self.num_heads, self.nope + self.v_dim, self.kv_lora)
+            w_uk = kvb[:, : self.nope, :].contiguous()                       # q_lat = q_nope @ W_UK
+            w_uv = kvb[:, self.nope:, :].transpose(1, 2).contiguous()        # out = out_lat @ W_UV
+            w = (w_uk, w_uv, self.kv_b_w.data_ptr())
+            self._w_abs = w
+        return w[0], w[1]
+
+    def _forward_absorbed(self, inp, q, kv_c, k_pe, cache):
+        """sm_100a path: multi-query attention over the latent cache (csrc/attn/mla_attention.cu). No host
+        synchronisation, so decode batches run inside CUDA graphs."""
+        from gllm_b200.ops import sm100
+        t, hl = q.shape[0], self.num_heads
+        w_uk, w_uv = self._absorbed_weights()
+        q_full = torch.empty(t, hl, 576, dtype=q.dtype, device=q.device)
+        q_lat = torch.bmm(q[:, :, : self.nope].transpose(0, 1), w_uk)        # [hl, T, 512]
+        q_full[:, :, :512].copy_(q_lat.transpose(0, 1))
+        sm100.mla_rope_cache(q[:, :, self.nope:], q_full, k_pe, kv_c, self.rope.cos_sin, inp.positions,
+                             inp.slot_mapping, cache)
+        splits = sm100.mla_splits(t, hl)
+        out_lat = sm100.mla_attention(q_full, cache, inp.block_table, inp.tok_seq, inp.positions, self.scaling,
+                                      splits=splits)
+        out = torch.bmm(out_lat.transpose(0, 1), w_uv)                        # [hl, T, v]
+        return out.transpose(0, 1).reshape(t, hl * self.v_dim)
 
 
 class DeepseekDecoderLayer(nn.Module):

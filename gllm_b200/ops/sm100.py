@@ -358,3 +358,59 @@ def linear_fp8_block(x: torch.Tensor, w8: torch.Tensor, w_scale_inv: torch.Tenso
                                 stream_ptr()), "gemm_fp8_block")
     _count()
     return out
+
+
+# ----------------------------------------------------------------------------------------------
+# multi-head latent attention (DeepSeek): absorbed MQA over the paged latent cache
+# ----------------------------------------------------------------------------------------------
+def mla_splits(tokens: int, heads: int) -> int:
+    """KV splits so that a decode batch still fills the machine (one CTA = 16 heads of one token)."""
+    ctas = max(1, tokens * ((heads + 15) // 16))
+    return max(1, min(16, 296 // ctas))
+
+
+def mla_rope_cache(q_pe: torch.Tensor, q_full: torch.Tensor, k_pe: torch.Tensor, kv_c: torch.Tensor,
+                   cos_sin: torch.Tensor, positions: torch.Tensor, slots: torch.Tensor, cache: torch.Tensor):
+    """q_pe [T,H,64] (strided view), q_full [T,H,576] (rope part written), k_pe [T,64], kv_c [T,512];
+    latent row -> cache [pages,1,9,page,64] at `slots`."""
+    t, h, r = q_pe.shape
+    assert r == 64 and q_pe.stride(2) == 1 and k_pe.stride(-1) == 1 and kv_c.stride(1) == 1 and kv_c.shape[1] == 512
+    assert q_full.is_contiguous() and q_full.shape == (t, h, 576) and cos_sin.dtype == torch.float32
+    if positions.dim() == 2:
+        positions = positions[0]
+    L = _lib.load()
+    check(L.gllm_mla_rope_cache(_p(q_pe), q_pe.stride(0), q_pe.stride(1), h, _p(q_full), _p(k_pe), k_pe.stride(0),
+                                _p(kv_c), kv_c.stride(0), _p(cos_sin), _p(positions), _p(slots), _p(cache),
+                                cache.shape[3], t, stream_ptr()), "mla_rope_cache")
+    _count()
+
+
+def mla_attention(q_full: torch.Tensor, cache: torch.Tensor, block_table: torch.Tensor,
+                  tok_seq: Optional[torch.Tensor], positions: torch.Tensor, scale: float,
+                  splits: Optional[int] = None) -> torch.Tensor:
+    """q_full [T,H,576] bf16 -> out_lat [T,H,512]; every token attends to keys [0, position]."""
+    t, h, d = q_full.shape
+    assert d == 576 and q_full.is_contiguous() and q_full.dtype == _BF16
+    pages, hkv, nslab, page_size, w = cache.shape
+    assert hkv == 1 and nslab == 9 and w == 64
+    if positions.dim() == 2:
+        positions = positions[0]
+    if splits is None:
+        splits = mla_splits(t, h)
+    out = torch.empty(t, h, 512, dtype=_BF16, device=q_full.device)
+    part_o = part_lse = None
+    if splits > 1:
+        key = ("mla_ws", q_full.device)
+        need = t * h * splits
+        ws = _attn_ws.get(key)
+        if ws is None or ws[0].numel() < need * 512:
+            ws = (torch.empty(need * 512, dtype=torch.float32, device=q_full.device),
+                  torch.empty(need, dtype=torch.float32, device=q_full.device))
+            _attn_ws[key] = ws
+        part_o, part_lse = ws
+    L = _lib.load()
+    check(L.gllm_mla_attention(_p(q_full), _p(out), _p(cache), pages, _p(block_table), _p(tok_seq), _p(positions),
+                               _p(part_o), _p(part_lse), t, block_table.shape[1], h, page_size, splits, float(scale),
+                               stream_ptr()), "mla_attention")
+    _count(2 if splits > 1 else 1)
+    return out

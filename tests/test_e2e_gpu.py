@@ -89,3 +89,34 @@ def test_qwen3_vl_gpu_matches_cpu_engine():
         llm.shutdown()
     # bf16 kernels vs the PyTorch oracle path on a random model: the first generated tokens must agree
     assert [x[0] for x in outs["cpu"]] == [x[0] for x in outs["cuda"]], outs
+
+
+def test_deepseek_mla_gpu_matches_cpu_engine():
+    """DeepSeek-V3 style model (MLA latent cache 512+64, grouped top-k MoE with a shared expert): the sm_100a
+    absorbed-MLA kernel path with CUDA graphs vs the PyTorch expanded-form oracle on the CPU."""
+    from gllm_b200 import LLM
+    cfg = {"architectures": ["DeepseekV3ForCausalLM"], "hidden_size": 256, "intermediate_size": 512,
+           "moe_intermediate_size": 128, "num_hidden_layers": 3, "num_attention_heads": 8, "num_key_value_heads": 8,
+           "n_routed_experts": 8, "n_shared_experts": 1, "num_experts_per_tok": 2, "n_group": 2, "topk_group": 1,
+           "first_k_dense_replace": 1, "routed_scaling_factor": 2.5, "norm_topk_prob": True, "q_lora_rank": 128,
+           "kv_lora_rank": 512, "qk_nope_head_dim": 128, "qk_rope_head_dim": 64, "v_head_dim": 128,
+           "vocab_size": 1024, "max_position_embeddings": 512, "eos_token_id": 1, "rms_norm_eps": 1e-6,
+           "rope_theta": 10000.0, "torch_dtype": "bfloat16", "scoring_func": "sigmoid", "topk_method": "noaux_tc"}
+    prompts = [[5, 9, 100, 7], list(range(20, 150)), [77] * 33]
+    outs, params, stats = {}, None, None
+    for dev in ("cpu", "cuda"):
+        torch.manual_seed(21)
+        llm = LLM(cfg, load_format="dummy", device=dev, maxp=64, maxd=16, model_max_length=256, log_stats=False,
+                  num_cpu_pages=64, num_gpu_pages=64, max_cuda_graph_bs=4)
+        model = llm.worker.runner.model
+        if params is None:
+            params = [(n, p.detach().cpu().clone()) for n, p in model.named_parameters()]
+        else:
+            for (n, p), (_, q) in zip(model.named_parameters(), params):
+                p.data.copy_(q.to(p.device))
+        o = llm.generate(tokens=prompts, output_lens=[6] * len(prompts), ignore_eos=True)
+        outs[dev] = [s.token_ids[-6:] for s in o]
+        stats = dict(llm.worker.runner.stats)
+        llm.shutdown()
+    assert stats["graph_steps"] > 0, "MLA decode did not run inside CUDA graphs"
+    assert [x[0] for x in outs["cpu"]] == [x[0] for x in outs["cuda"]], outs

@@ -404,3 +404,89 @@ def test_gemm_splitk_silu(m):
     h = x.float() @ w.float().t()
     yr = torch.nn.functional.silu(h[:, :i]) * h[:, i:]
     assert _rel_err(y, yr) < 1e-2
+
+
+def _mla_ref(q_full, cache, bt, tok_seq, positions, scale):
+    t, h, _ = q_full.shape
+    out = torch.zeros(t, h, 512, dtype=torch.float32, device=q_full.device)
+    for i in range(t):
+        s = int(tok_seq[i]) if tok_seq is not None else i
+        n = int(positions[i]) + 1
+        lat = ref.gather_kv(cache, bt[s], n)[:, 0].float()          # [n, 576]
+        att = torch.softmax((q_full[i].float() @ lat.t()) * scale, dim=-1)
+        out[i] = att @ lat[:, :512]
+    return out
+
+
+@pytest.mark.parametrize("heads", [16, 8, 40])
+@pytest.mark.parametrize("splits", [1, 3, None])
+def test_mla_attention_decode(heads, splits):
+    from gllm_b200.ops import sm100
+    torch.manual_seed(7)
+    page, b = 16, 5
+    lens = [1, 63, 64, 300, 777]
+    max_blocks = max((n + page - 1) // page for n in lens) + 1
+    n_pages = sum((n + page - 1) // page for n in lens) + 2
+    cache = (torch.randn(n_pages, 1, 9, page, 64, device=_dev()) * 0.5).bfloat16()
+    perm = torch.randperm(n_pages)[: n_pages - 1].tolist()
+    bt = torch.zeros(b, max_blocks, dtype=torch.int32)
+    c = 0
+    for i, n in enumerate(lens):
+        k = (n + page - 1) // page
+        bt[i, :k] = torch.tensor(perm[c:c + k], dtype=torch.int32)
+        c += k
+    bt = bt.to(_dev())
+    q = (torch.randn(b, heads, 576, device=_dev()) * 0.3).bfloat16()
+    pos = torch.tensor([n - 1 for n in lens], dtype=torch.int32, device=_dev())
+    scale = 192 ** -0.5
+    out = sm100.mla_attention(q, cache, bt, None, pos, scale, splits=splits)
+    want = _mla_ref(q, cache, bt, None, pos, scale)
+    assert _rel_err(out, want) < 1.5e-2, _rel_err(out, want)
+
+
+def test_mla_attention_prefill_tokens_and_rope_cache():
+    """Mixed batch: every token attends to its own causal prefix (tok_seq / positions); plus the fused
+    rope + latent-cache write against the PyTorch oracle ops."""
+    from gllm_b200.ops import sm100
+    torch.manual_seed(8)
+    page, heads = 16, 16
+    q_lens, ctx = [40, 1, 70], [0, 130, 25]          # new tokens / already cached tokens per sequence
+    b = len(q_lens)
+    tot = [q + c for q, c in zip(q_lens, ctx)]
+    max_blocks = max((n + page - 1) // page for n in tot) + 1
+    n_pages = sum((n + page - 1) // page for n in tot) + 1
+    cache = (torch.randn(n_pages, 1, 9, page, 64, device=_dev()) * 0.5).bfloat16()
+    bt = torch.zeros(b, max_blocks, dtype=torch.int32)
+    c = 0
+    for i, n in enumerate(tot):
+        k = (n + page - 1) // page
+        bt[i, :k] = torch.arange(c, c + k, dtype=torch.int32)
+        c += k
+    tok_seq = torch.tensor(sum(([i] * q for i, q in enumerate(q_lens)), []), dtype=torch.int32)
+    pos = torch.tensor(sum((list(range(cx, cx + q)) for q, cx in zip(q_lens, ctx)), []), dtype=torch.int32)
+    t = int(tok_seq.numel())
+    slots = torch.tensor([int(bt[s, p // page]) * page + p % page for s, p in zip(tok_seq.tolist(), pos.tolist())],
+                         dtype=torch.int32)
+    bt, tok_seq, pos, slots = bt.to(_dev()), tok_seq.to(_dev()), pos.to(_dev()), slots.to(_dev())
+    # ---- rope + cache write ----
+    qk_dim, nope = 192, 128
+    qp = (torch.randn(t, heads, qk_dim, device=_dev()) * 0.5).bfloat16()
+    kv_a = (torch.randn(t, 576, device=_dev()) * 0.5).bfloat16()
+    kv_c = kv_a[:, :512].contiguous()
+    cs = ref.build_cos_sin_cache(64, 512, 10000.0).to(_dev())
+    q_full = torch.zeros(t, heads, 576, dtype=torch.bfloat16, device=_dev())
+    cache2 = cache.clone()
+    sm100.mla_rope_cache(qp[:, :, nope:], q_full, kv_a[:, 512:], kv_c, cs, pos, slots, cache2)
+    q_pe = qp[:, :, nope:].contiguous()
+    k_pe = kv_a[:, 512:].contiguous().view(t, 1, 64)
+    ref.rope_kv_write(q_pe, k_pe, None, pos, cs, 64, False, None, None, 1e-6, None, None, None)
+    cache_ref = cache.clone()
+    ref.write_kv_cache(torch.cat([kv_c, k_pe.view(t, 64)], -1).view(t, 1, 576), None, cache_ref, None, slots)
+    assert _rel_err(q_full[:, :, 512:], q_pe) < 8e-3
+    assert _rel_err(cache2, cache_ref) < 8e-3
+    # ---- attention over the freshly written cache ----
+    q_full[:, :, :512] = (torch.randn(t, heads, 512, device=_dev()) * 0.3).bfloat16()
+    scale = 192 ** -0.5
+    out = sm100.mla_attention(q_full, cache2, bt, tok_seq, pos, scale)
+    want = _mla_ref(q_full, cache2, bt, tok_seq, pos, scale)
+    assert _rel_err(out, want) < 1.5e-2, _rel_err(out, want)

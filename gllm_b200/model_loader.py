@@ -77,6 +77,8 @@ class ModelLoader:
         else:
             reader = CheckpointReader(self.model_path)
             model.load_weights(reader, progress)
+        if hasattr(model, "process_weights"):
+            model.process_weights()
         n_bytes = sum(p.numel() * p.element_size() for p in model.parameters())
         logger.info("model %s: %.2f GB of weights on this rank", self.architecture, n_bytes / 2 ** 30)
         return model

@@ -107,17 +107,26 @@ class MLAAttention(nn.Module):
             out[q0:q1] = torch.einsum("hqk,khd->qhd", torch.softmax(att, -1), v.float()).to(h.dtype)
         return out.view(t, hl * self.v_dim)
 
+    def process_weights(self):
+        """W_UK [hl, nope, 512] and W_UV [hl, 512, v] views of kv_b_proj, made contiguous once, eagerly, after
+        the weights are final and BEFORE any CUDA-graph capture (tensors created inside a capture only get
+        their contents when the graph replays). Reference: MLAAttention.process_weights,
+        gllm/layers/attention.py:106-127."""
+        kvb = self.kv_b_w.data.view(self.num_heads, self.nope + self.v_dim, self.kv_lora)
+        w_uk, w_uv = kvb[:, : self.nope, :], kvb[:, self.nope:, :].transpose(1, 2)
+        old = getattr(self, "_w_abs", None)
+        if old is not None:   # keep the addresses: captured CUDA graphs point at these tensors
+            old[0].copy_(w_uk)
+            old[1].copy_(w_uv)
+        else:
+            self._w_abs = (w_uk.contiguous(),    # q_lat = q_nope @ W_UK
+                           w_uv.contiguous())    # out   = out_lat @ W_UV
+
     def _absorbed_weights(self):
-        """W_UK [hl, nope, 512] and W_UV [hl, 512, v] views of kv_b_proj, made contiguous once
-        (reference: MLAAttention.process_weights, gllm/layers/attention.py:106-127)."""
-        w = getattr(self, "_w_abs", None)
-        if w is None or w[2] != self.kv_b_w.data_ptr():
-            kvb = self.kv_b_w.data.view(self.num_heads, self.nope + self.v_dim, self.kv_lora)
-            w_uk = kvb[:, : self.nope, :].contiguous()                       # q_lat = q_nope @ W_UK
-            w_uv = kvb[:, self.nope:, :].transpose(1, 2).contiguous()        # out = out_lat @ W_UV
-            w = (w_uk, w_uv, self.kv_b_w.data_ptr())
-            self._w_abs = w
-        return w[0], w[1]
+        if getattr(self, "_w_abs", None) is None:
+            assert not torch.cuda.is_current_stream_capturing(), "call model.process_weights() before capture"
+            self.process_weights()
+        return self._w_abs
 
     def _forward_absorbed(self, inp, q, kv_c, k_pe, cache):
         """sm_100a path: multi-query attention over the latent cache (csrc/attn/mla_attention.cu). No host
@@ -165,6 +174,12 @@ class DeepseekDecoderLayer(nn.Module):
 
 
 class DeepseekForCausalLM(CausalLM):
+    def process_weights(self):
+        """Post-load weight preparation (absorbed MLA matrices); the runner calls it before graph capture."""
+        if self.device.type == "cuda":
+            for layer in self.layers:
+                layer.attn.process_weights()
+
     def __init__(self, spec: ModelSpec, device="cpu"):
         # build the generic skeleton with zero layers, then install MLA layers
         nn.Module.__init__(self)

@@ -108,9 +108,29 @@ def bench_attn():
                           "tflops": round(flops / ms / 1e9, 1)}), flush=True)
 
 
+def bench_mla():
+    """DeepSeek MLA decode over the latent cache: bytes = latent rows read once per 16-head group."""
+    page = 16
+    for b, ctx, heads in ((64, 4096, 16), (256, 2048, 16), (32, 4096, 128)):
+        n_pages = b * (ctx // page) + 1
+        cache = (torch.randn(n_pages, 1, 9, page, 64, device="cuda") * 0.3).bfloat16()
+        bt = torch.arange(b * (ctx // page), device="cuda", dtype=torch.int32).view(b, -1).contiguous()
+        pos = torch.full((b,), ctx - 1, device="cuda", dtype=torch.int32)
+        q = (torch.randn(b, heads, 576, device="cuda") * 0.3).bfloat16()
+        ms = timeit(lambda: sm100.mla_attention(q, cache, bt, None, pos, 192 ** -0.5), iters=10)
+        groups = (heads + 15) // 16
+        byts = 1.0 * b * ctx * 576 * 2 * groups
+        flops = 2.0 * b * ctx * heads * (576 + 512)
+        print(json.dumps({"kernel": "mla_decode", "B": b, "ctx": ctx, "heads": heads, "ms": round(ms, 4),
+                          "gbs_incl_group_rereads": round(byts / ms / 1e6, 1), "tflops": round(flops / ms / 1e9, 1),
+                          "unique_latent_gbs": round(byts / groups / ms / 1e6, 1)}), flush=True)
+
+
 if __name__ == "__main__":
     what = sys.argv[1] if len(sys.argv) > 1 else "all"
     if what in ("gemm", "all"):
         bench_gemm()
     if what in ("attn", "all"):
         bench_attn()
+    if what in ("mla", "all"):
+        bench_mla()

@@ -32,8 +32,15 @@ struct Fp8Params {
   int ldc;
   const float* a_s;  // [K/128, M]
   int lda_s;         // = M (row pitch of a_s)
-  const float* w_s;  // [N/128, K/128]
+  const float* w_s;  // [N/128, K/128]  (grouped: [E][N/64][K/128], one scale row per 64 weight rows)
   const __nv_bfloat16* bias;
+  // grouped (MoE) mode: M tile t multiplies the e4m3 slab of expert tile_expert[t]; the weight scales are
+  // stored per 64-row half tile so a [64 gate | 64 up] interleaved tile can carry two different block scales
+  const int32_t* tile_expert;
+  const int32_t* num_m_tiles_ptr;
+  int n_per_expert;      // rows of one expert slab
+  int64_t ws_stride_e;   // floats per expert in w_s
+  int silu;              // 1: out[:, j] = silu(acc[j]) * acc[64 + j]  (64 output columns per tile)
 };
 
 __global__ void __launch_bounds__(kFThreads, 1)
@@ -49,7 +56,10 @@ gemm_fp8_block_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int num_m = (p.M + kFBM - 1) / kFBM, num_n = (p.N + kFBN - 1) / kFBN;
+  const bool grouped = p.tile_expert != nullptr;
+  const int num_m = p.num_m_tiles_ptr != nullptr ? min(*p.num_m_tiles_ptr, (p.M + kFBM - 1) / kFBM)
+                                                 : (p.M + kFBM - 1) / kFBM;
+  const int num_n = (p.N + kFBN - 1) / kFBN;
   const int num_tiles = num_m * num_n;
   const int num_kb = p.K / kFBK;
 
@@ -71,13 +81,14 @@ gemm_fp8_block_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
       uint32_t it = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int m0 = (tile % num_m) * kFBM, n0 = (tile / num_m) * kFBN;
+        const int b_row_off = grouped ? p.tile_expert[tile % num_m] * p.n_per_expert : 0;
         for (int kb = 0; kb < num_kb; ++kb, ++it) {
           const int s = it % kFStages;
           mbar_wait(&empty_bar[s], ((it / kFStages) & 1) ^ 1);
           uint8_t* sa = smem + s * kStageBytes;
           mbar_expect_tx(&full_bar[s], kStageBytes);
           tma_load_2d(sa, &tmap_a, &full_bar[s], kb * kFBK, m0, kEvictNormal);
-          tma_load_2d(sa + kABytes, &tmap_b, &full_bar[s], kb * kFBK, n0, kEvictNormal);
+          tma_load_2d(sa + kABytes, &tmap_b, &full_bar[s], kb * kFBK, n0 + b_row_off, kEvictNormal);
         }
       }
     }
@@ -117,8 +128,15 @@ gemm_fp8_block_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
       for (int kb = 0; kb < num_kb; ++kb, ++it) {
         const uint32_t buf = it & 1;
         const float sa = row_ok ? p.a_s[static_cast<size_t>(kb) * p.lda_s + row] : 0.f;
-        const float sw = p.w_s[static_cast<size_t>(n0 / kFBN) * num_kb + kb];
-        const float sc = sa * sw;
+        float sc, sc_hi;
+        if (grouped) {
+          const float* ws = p.w_s + static_cast<size_t>(p.tile_expert[tile % num_m]) * p.ws_stride_e +
+                            static_cast<size_t>(n0 / 64) * num_kb + kb;
+          sc = sa * ws[0];
+          sc_hi = sa * ws[num_kb];
+        } else {
+          sc = sc_hi = sa * p.w_s[static_cast<size_t>(n0 / kFBN) * num_kb + kb];
+        }
         mbar_wait(&tmem_full[buf], (it >> 1) & 1);
         tc_fence_after();
         const uint32_t t_row = tmem_base + buf * kFBN + (static_cast<uint32_t>(q * 32) << 16);
@@ -128,13 +146,29 @@ gemm_fp8_block_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
           tmem_ld_32x32(t_row + c, v);
           tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 32; ++j) acc[c + j] = fmaf(__uint_as_float(v[j]), sc, acc[c + j]);
+          for (int j = 0; j < 32; ++j) acc[c + j] = fmaf(__uint_as_float(v[j]), c < 64 ? sc : sc_hi, acc[c + j]);
         }
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&tmem_empty[buf]);
       }
-      if (row_ok) {
+      if (row_ok && p.silu) {
+        __nv_bfloat16* crow = p.C + static_cast<size_t>(row) * p.ldc;
+#pragma unroll
+        for (int c = 0; c < 64; c += 8) {
+          const int col = n0 / 2 + c;
+          if (col < p.N / 2) {
+            float f[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              const float gv = acc[c + e];
+              f[e] = gv / (1.0f + __expf(-gv)) * acc[64 + c + e];
+            }
+            st_v4(crow + col, make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]),
+                                         pack_bf16(f[6], f[7])));
+          }
+        }
+      } else if (row_ok) {
         __nv_bfloat16* crow = p.C + static_cast<size_t>(row) * p.ldc;
 #pragma unroll
         for (int c = 0; c < kFBN; c += 8) {
@@ -221,6 +255,7 @@ GLLM_EXPORT int gllm_gemm_fp8_block(const void* A8, const void* a_s, const void*
   p.lda_s = M;
   p.w_s = reinterpret_cast<const float*>(w_s);
   p.bias = reinterpret_cast<const __nv_bfloat16*>(bias);
+  p.tile_expert = nullptr; p.num_m_tiles_ptr = nullptr; p.n_per_expert = 0; p.ws_stride_e = 0; p.silu = 0;
   constexpr int smem_bytes = kFStages * (kFBM * kFBK + kFBN * kFBK) + 1024 + 256;
   static bool configured = false;
   if (!configured) {
@@ -228,6 +263,43 @@ GLLM_EXPORT int gllm_gemm_fp8_block(const void* A8, const void* a_s, const void*
     configured = true;
   }
   const int tiles = ((M + kFBM - 1) / kFBM) * ((N + kFBN - 1) / kFBN);
+  const int grid = tiles < num_sms() ? tiles : num_sms();
+  gemm_fp8_block_kernel<<<grid, kFThreads, smem_bytes, reinterpret_cast<cudaStream_t>(stream)>>>(ta, tb, p);
+  CUDA_CHECK_RET(cudaGetLastError());
+  return 0;
+}
+
+// Grouped (MoE) block-scaled fp8 GEMM: A8 [max_tiles*128, K] e4m3 (expert-sorted, 128-row tiles), a_s
+// [K/128, max_tiles*128]; W8 [E, N, K] e4m3, w_s [E, N/64, K/128] (one scale row per 64 weight rows);
+// epi 1 = SiLU gate on [64 gate | 64 up] interleaved tiles -> C [rows, N/2].
+GLLM_EXPORT int gllm_moe_grouped_gemm_fp8(const void* A8, const void* a_s, const void* W8, const void* w_s, void* C,
+                                          int64_t ldc, int max_tiles, int N, int K, int E, const void* tile_expert,
+                                          const void* num_tiles_ptr, int epi, void* stream) {
+  if (max_tiles <= 0) return 0;
+  if (K % 128 != 0 || N % 128 != 0) {
+    fprintf(stderr, "[gllm_b200] moe_grouped_gemm_fp8: K %% 128 and N %% 128 required\n");
+    return 1;
+  }
+  const int M = max_tiles * kFBM;
+  CUtensorMap ta, tb;
+  if (make_tmap_2d(&ta, A8, M, K, K, kFBM, kFBK, CU_TENSOR_MAP_DATA_TYPE_UINT8)) return 1;
+  if (make_tmap_2d(&tb, W8, static_cast<uint64_t>(E) * N, K, K, kFBN, kFBK, CU_TENSOR_MAP_DATA_TYPE_UINT8)) return 1;
+  Fp8Params p;
+  p.M = M; p.N = N; p.K = K;
+  p.C = reinterpret_cast<__nv_bfloat16*>(C);
+  p.ldc = static_cast<int>(ldc);
+  p.a_s = reinterpret_cast<const float*>(a_s);
+  p.lda_s = M;
+  p.w_s = reinterpret_cast<const float*>(w_s);
+  p.bias = nullptr;
+  p.tile_expert = reinterpret_cast<const int32_t*>(tile_expert);
+  p.num_m_tiles_ptr = reinterpret_cast<const int32_t*>(num_tiles_ptr);
+  p.n_per_expert = N;
+  p.ws_stride_e = static_cast<int64_t>(N / 64) * (K / 128);
+  p.silu = epi == 1 ? 1 : 0;
+  constexpr int smem_bytes = kFStages * (kFBM * kFBK + kFBN * kFBK) + 1024 + 256;
+  CUDA_CHECK_RET(cudaFuncSetAttribute(gemm_fp8_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+  const int tiles = max_tiles * (N / kFBN);
   const int grid = tiles < num_sms() ? tiles : num_sms();
   gemm_fp8_block_kernel<<<grid, kFThreads, smem_bytes, reinterpret_cast<cudaStream_t>(stream)>>>(ta, tb, p);
   CUDA_CHECK_RET(cudaGetLastError());

@@ -30,8 +30,10 @@ def _param(*shape, dtype, device):
 class FusedMoE(nn.Module):
     def __init__(self, num_experts: int, top_k: int, hidden: int, intermediate: int, dtype, device,
                  renormalize: bool = True, use_ep: Optional[bool] = None, scoring: str = "softmax",
-                 n_group: int = 0, topk_group: int = 0, routed_scaling: float = 1.0, bias_correction: bool = False):
+                 n_group: int = 0, topk_group: int = 0, routed_scaling: float = 1.0, bias_correction: bool = False,
+                 quant: Optional[str] = None):
         super().__init__()
+        self.quant = quant if (quant == "fp8" and hidden % 128 == 0) else None
         st = ps.get_state()
         self.num_experts, self.top_k, self.hidden = num_experts, top_k, hidden
         self.renormalize, self.scoring = renormalize, scoring
@@ -51,8 +53,23 @@ class FusedMoE(nn.Module):
             self.expert_map = None
         self.router_w = _param(num_experts, hidden, dtype=dtype, device=device)
         self.e_bias = _param(num_experts, dtype=torch.float32, device=device) if bias_correction else None
-        self.w13 = _param(self.e_local, 2 * self.inter, hidden, dtype=dtype, device=device)
-        self.w2 = _param(self.e_local, hidden, self.inter, dtype=dtype, device=device)
+        if self.quant == "fp8" and self.inter % 128 != 0:
+            self.quant = None
+        if self.quant == "fp8":
+            # block-scaled e4m3 experts (reference: Fp8MoEMethod, fused_moe_triton/layer.py:99-194); scales are
+            # kept per 64 weight rows so an interleaved [64 gate | 64 up] GEMM tile can carry two block scales
+            f8 = torch.float8_e4m3fn
+            self.w13 = nn.Parameter(torch.zeros(self.e_local, 2 * self.inter, hidden, dtype=f8, device=device),
+                                    requires_grad=False)
+            self.w2 = nn.Parameter(torch.zeros(self.e_local, hidden, self.inter, dtype=f8, device=device),
+                                   requires_grad=False)
+            self.w13_ws = nn.Parameter(torch.ones(self.e_local, 2 * self.inter // 64, hidden // 128,
+                                                  dtype=torch.float32, device=device), requires_grad=False)
+            self.w2_ws = nn.Parameter(torch.ones(self.e_local, hidden // 64, self.inter // 128,
+                                                 dtype=torch.float32, device=device), requires_grad=False)
+        else:
+            self.w13 = _param(self.e_local, 2 * self.inter, hidden, dtype=dtype, device=device)
+            self.w2 = _param(self.e_local, hidden, self.inter, dtype=dtype, device=device)
 
     # -- routing ----------------------------------------------------------------------------------
     def route(self, h: torch.Tensor):
@@ -68,6 +85,14 @@ class FusedMoE(nn.Module):
 
     def forward(self, h: torch.Tensor, tpc=None) -> torch.Tensor:
         w, ids = self.route(h)
+        if self.quant == "fp8":
+            if h.is_cuda:
+                from gllm_b200.ops import sm100_moe
+                return sm100_moe.fused_experts_fp8(h, self.w13, self.w13_ws, self.w2, self.w2_ws, w, ids,
+                                                   self.expert_map)
+            w13 = (self.w13.float() * self.w13_ws.repeat_interleave(64, 1).repeat_interleave(128, 2)).to(h.dtype)
+            w2 = (self.w2.float() * self.w2_ws.repeat_interleave(64, 1).repeat_interleave(128, 2)).to(h.dtype)
+            return ref.fused_experts(h, w13, w2, w, ids, self.expert_map)
         if h.is_cuda:
             from gllm_b200.ops import sm100_moe
             return sm100_moe.fused_experts(h, self.w13, self.w2, w, ids, self.expert_map)
@@ -84,12 +109,38 @@ class FusedMoE(nn.Module):
         else:
             gu = wu.shard_gate_up(gate, up, self.tp_rank, self.tp_size)
             down = wu.shard_cols(down, self.tp_rank, self.tp_size)
+        if self.quant == "fp8":
+            q13, s13 = _block_quant_rows64(gu)
+            q2, s2 = _block_quant_rows64(down)
+            if self.w13.is_cuda:
+                q13 = ref.interleave_gate_up(q13.view(torch.uint8), 64).view(torch.float8_e4m3fn)
+                s13 = ref.interleave_gate_up(s13, 1)
+            self.w13.data[le].copy_(q13)
+            self.w13_ws.data[le].copy_(s13)
+            self.w2.data[le].copy_(q2)
+            self.w2_ws.data[le].copy_(s2)
+            return
         if self.w13.is_cuda:
             # the grouped GEMM's SiLU-gate epilogue wants gate/up rows interleaved per 64
             assert self.inter % 64 == 0, "sm_100a MoE path needs intermediate % 64 == 0"
             gu = ref.interleave_gate_up(gu, 64)
         self.w13.data[le].copy_(gu)
         self.w2.data[le].copy_(down)
+
+
+def _block_quant_rows64(w: torch.Tensor):
+    """[N, K] -> (e4m3 [N, K], fp32 scales [N/64, K/128]): 128x128 block quantisation (scale = amax / 448) of
+    the checkpoint layout, scales repeated per 64-row half block. Lossless for a de-quantised fp8 checkpoint
+    whose blocks are aligned (N, K multiples of 128)."""
+    w = w.float()
+    n, k = w.shape
+    nb, kb = (n + 127) // 128, (k + 127) // 128
+    wp = torch.zeros(nb * 128, kb * 128, dtype=torch.float32, device=w.device)
+    wp[:n, :k] = w
+    blk = wp.view(nb, 128, kb, 128)
+    sc = (blk.abs().amax(dim=(1, 3)) / 448.0).clamp_min(1e-12)
+    q = (blk / sc.view(nb, 1, kb, 1)).view(nb * 128, kb * 128)[:n, :k].to(torch.float8_e4m3fn)
+    return q, sc.repeat_interleave(2, 0)[: (n + 63) // 64]
 
 
 def _sm_grouped_topk(moe: FusedMoE, logits):
@@ -108,7 +159,7 @@ class SparseMoeBlock(nn.Module):
         self.experts = FusedMoE(m.num_experts, m.top_k, spec.hidden_size, m.intermediate_size, spec.dtype, device,
                                 renormalize=m.norm_topk_prob, scoring=m.scoring, n_group=m.n_group,
                                 topk_group=m.topk_group, routed_scaling=m.routed_scaling,
-                                bias_correction=m.has_bias_correction)
+                                bias_correction=m.has_bias_correction, quant=getattr(spec, "quant", None))
         self.shared = None
         self.shared_gate_w = None
         if m.shared_intermediate_size > 0:

@@ -72,6 +72,7 @@ def _declare(lib):
     sig("gllm_moe_grouped_gemm", [P, L, P, P, L, I, I, I, I, P, P, I, P, P])
     sig("gllm_moe_combine", [P, P, P, P, I, I, I, P])
     sig("gllm_fp8_quant_group", [P, L, P, P, I, I, P])
+    sig("gllm_moe_grouped_gemm_fp8", [P, P, P, P, P, L, I, I, I, I, P, P, I, P])
     sig("gllm_gemm_fp8_block", [P, P, P, P, P, L, I, I, I, P, P])
 
 

@@ -388,7 +388,7 @@ class FusedTPComm(TPComm):
     def can_a2a(self, block) -> bool:
         ex = getattr(block, "experts", None)
         return (not self.small and ex is not None and ex.use_ep and getattr(block, "shared", None) is None
-                and ex.w13.is_cuda and ex.top_k <= 63)
+                and ex.w13.is_cuda and ex.w13.dtype == torch.bfloat16 and ex.top_k <= 63)
 
     def moe_add_norm(self, block, h, residual, norm_w, eps):
         """MoE block + residual add + next RMSNorm. Routed experts only (no shared expert) and EP:

@@ -205,3 +205,28 @@ def test_fp8_block_quantised_model_close_to_hf():
     same_first = sum(s.token_ids[len(p)] == _hf_greedy(m, p, 1)[0] for p, s in zip(PROMPTS, outs))
     assert same_first >= len(PROMPTS) - 1
     llm.shutdown()
+
+
+def test_fp8_block_quantised_moe_experts_close_to_hf():
+    """fp8 checkpoints also keep the MoE EXPERT weights block-quantised (e4m3 + a scale row per 64 weight rows,
+    reference Fp8MoEMethod): first tokens must agree with the unquantised HF model."""
+    import json
+    from transformers import Qwen3MoeConfig, Qwen3MoeForCausalLM
+    torch.manual_seed(12)
+    cfg = Qwen3MoeConfig(hidden_size=256, intermediate_size=512, moe_intermediate_size=128, num_hidden_layers=2,
+                         num_attention_heads=4, num_key_value_heads=2, head_dim=64, vocab_size=512,
+                         max_position_embeddings=512, eos_token_id=1, tie_word_embeddings=False, num_experts=4,
+                         num_experts_per_tok=2, decoder_sparse_step=1, mlp_only_layers=[], norm_topk_prob=True)
+    m = Qwen3MoeForCausalLM(cfg).eval().float()
+    d = _save(m)
+    c = json.load(open(os.path.join(d, "config.json")))
+    c["quantization_config"] = {"quant_method": "fp8", "activation_scheme": "dynamic", "fmt": "e4m3",
+                                "weight_block_size": [128, 128]}
+    json.dump(c, open(os.path.join(d, "config.json"), "w"))
+    llm = _engine(d)
+    ex = llm.worker.runner.model.layers[0].mlp.experts
+    assert ex.quant == "fp8" and ex.w13.dtype == torch.float8_e4m3fn and ex.w13_ws.shape == (4, 4, 2)
+    outs = llm.generate(tokens=PROMPTS, output_lens=[4] * len(PROMPTS), ignore_eos=True)
+    same_first = sum(s.token_ids[len(p)] == _hf_greedy(m, p, 1)[0] for p, s in zip(PROMPTS, outs))
+    assert same_first >= len(PROMPTS) - 1
+    llm.shutdown()

@@ -72,8 +72,27 @@ class FusedMoE(nn.Module):
             self.w2 = _param(self.e_local, hidden, self.inter, dtype=dtype, device=device)
 
     # -- routing ----------------------------------------------------------------------------------
+    def process_weights(self):
+        """The tcgen05 GEMM wants N % 8 == 0: expert counts like 60 (Qwen1.5-MoE) get a zero-padded router
+        weight, built once after loading (before CUDA-graph capture); the logits are sliced back to E columns."""
+        if self.router_w.is_cuda and self.num_experts % 8 != 0:
+            e_pad = (self.num_experts + 7) // 8 * 8
+            old = getattr(self, "_router_pad", None)
+            if old is None:
+                old = torch.zeros(e_pad, self.hidden, dtype=self.router_w.dtype, device=self.router_w.device)
+                self._router_pad = old
+            old[: self.num_experts].copy_(self.router_w.data)
+
+    def _router_logits(self, h: torch.Tensor) -> torch.Tensor:
+        if h.is_cuda and self.num_experts % 8 != 0:
+            if getattr(self, "_router_pad", None) is None:
+                assert not torch.cuda.is_current_stream_capturing(), "call model.process_weights() before capture"
+                self.process_weights()
+            return Fn.linear(h, self._router_pad)[:, : self.num_experts]
+        return Fn.linear(h, self.router_w)
+
     def route(self, h: torch.Tensor):
-        logits = Fn.linear(h, self.router_w)
+        logits = self._router_logits(h)
         if self.n_group > 0:
             return ref.grouped_topk(logits, self.top_k, self.renormalize, self.n_group, self.topk_group,
                                     self.scoring, self.e_bias, self.routed_scaling) if not h.is_cuda else \

@@ -365,6 +365,13 @@ class CausalLM(nn.Module):
         return tpc.gather_logits(local, self.spec.vocab_size)
 
     # -- weights ----------------------------------------------------------------------------------
+    def process_weights(self):
+        """Post-load preparation of derived tensors (padded routers, absorbed MLA matrices, ...): every
+        sub-module that defines `process_weights` is visited. Runs after loading, before graph capture."""
+        for m in self.modules():
+            if m is not self and hasattr(m, "process_weights"):
+                m.process_weights()
+
     def init_dummy(self, seed: int = 0):
         """`--load-format dummy`: random weights of the right shapes (reference: model_loader.py:154)."""
         g = torch.Generator(device="cpu").manual_seed(seed + 1000 * self.tp_rank + 7 * ps.get_pp_rank())

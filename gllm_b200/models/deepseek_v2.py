@@ -112,6 +112,8 @@ class MLAAttention(nn.Module):
         the weights are final and BEFORE any CUDA-graph capture (tensors created inside a capture only get
         their contents when the graph replays). Reference: MLAAttention.process_weights,
         gllm/layers/attention.py:106-127."""
+        if not self.kv_b_w.is_cuda:
+            return
         kvb = self.kv_b_w.data.view(self.num_heads, self.nope + self.v_dim, self.kv_lora)
         w_uk, w_uv = kvb[:, : self.nope, :], kvb[:, self.nope:, :].transpose(1, 2)
         old = getattr(self, "_w_abs", None)
@@ -174,12 +176,6 @@ class DeepseekDecoderLayer(nn.Module):
 
 
 class DeepseekForCausalLM(CausalLM):
-    def process_weights(self):
-        """Post-load weight preparation (absorbed MLA matrices); the runner calls it before graph capture."""
-        if self.device.type == "cuda":
-            for layer in self.layers:
-                layer.attn.process_weights()
-
     def __init__(self, spec: ModelSpec, device="cpu"):
         # build the generic skeleton with zero layers, then install MLA layers
         nn.Module.__init__(self)

@@ -126,3 +126,57 @@ def test_deepseek_mla_gpu_matches_cpu_engine():
     assert [x[0] for x in outs["cpu"]] == [x[0] for x in outs["cuda"]], outs
     # decode steps (CUDA graphs on the GPU) must agree too on most sequences (bf16 near-ties may flip late tokens)
     assert sum(a == b for a, b in zip(outs["cpu"], outs["cuda"])) >= 2, outs
+
+
+def _family_cfgs():
+    from gllm_b200.models.presets import tiny
+    base = dict(hidden_size=256, num_hidden_layers=2, num_attention_heads=4, num_key_value_heads=2, head_dim=64,
+                intermediate_size=512, vocab_size=1024, torch_dtype="bfloat16")
+    return {
+        "llama": tiny("LlamaForCausalLM", **base),
+        "qwen2-bias-tied": tiny("Qwen2ForCausalLM", **{**base, "tie_word_embeddings": True}),
+        "mixtral": tiny("MixtralForCausalLM", **{**base, "intermediate_size": 256, "num_local_experts": 4,
+                                                  "num_experts_per_tok": 2}),
+        "qwen3-moe": tiny("Qwen3MoeForCausalLM", **{**base, "moe_intermediate_size": 128, "num_experts": 8,
+                                                    "num_experts_per_tok": 2, "decoder_sparse_step": 1,
+                                                    "mlp_only_layers": [], "norm_topk_prob": True}),
+        "qwen2-moe-shared": tiny("Qwen2MoeForCausalLM", **{**base, "moe_intermediate_size": 128, "num_experts": 4,
+                                                           "num_experts_per_tok": 2, "decoder_sparse_step": 1,
+                                                           "mlp_only_layers": [],
+                                                           "shared_expert_intermediate_size": 256}),
+        "chatglm": {"architectures": ["ChatGLMModel"], "hidden_size": 256, "num_layers": 2, "num_attention_heads": 4,
+                    "multi_query_attention": True, "multi_query_group_num": 2, "kv_channels": 64,
+                    "ffn_hidden_size": 512, "padded_vocab_size": 1024, "layernorm_epsilon": 1e-5,
+                    "add_qkv_bias": True, "seq_length": 512, "torch_dtype": "bfloat16", "eos_token_id": 1},
+    }
+
+
+@pytest.mark.parametrize("family", ["llama", "qwen2-bias-tied", "mixtral", "qwen3-moe", "qwen2-moe-shared", "chatglm"])
+def test_model_families_gpu_match_cpu_engine(family):
+    """Every decoder family through the GPU engine (native kernels + CUDA graphs) vs the CPU oracle engine with
+    the same weights (MoE w13 is stored gate/up-interleaved per 64 rows on the GPU)."""
+    from gllm_b200 import LLM
+    from gllm_b200.ops import ref
+    cfg = _family_cfgs()[family]
+    prompts = [[5, 9, 100, 7], list(range(20, 120)), [77] * 33]
+    outs, params = {}, None
+    for dev in ("cpu", "cuda"):
+        torch.manual_seed(31)
+        llm = LLM(cfg, load_format="dummy", device=dev, maxp=64, maxd=16, model_max_length=256, log_stats=False,
+                  num_cpu_pages=64, num_gpu_pages=64, max_cuda_graph_bs=4)
+        model = llm.worker.runner.model
+        if params is None:
+            params = [(n, p.detach().cpu().clone()) for n, p in model.named_parameters()]
+        else:
+            for (n, p), (_, q) in zip(model.named_parameters(), params):
+                if n.endswith("experts.w13"):
+                    q = torch.stack([ref.interleave_gate_up(q[e], 64) for e in range(q.shape[0])])
+                p.data.copy_(q.to(p.device))
+            model.process_weights()
+        o = llm.generate(tokens=prompts, output_lens=[5] * len(prompts), ignore_eos=True)
+        outs[dev] = [s.token_ids[-5:] for s in o]
+        if dev == "cuda":
+            assert llm.worker.runner.stats["graph_steps"] > 0
+        llm.shutdown()
+    assert [x[0] for x in outs["cpu"]] == [x[0] for x in outs["cuda"]], outs
+    assert sum(a == b for a, b in zip(outs["cpu"], outs["cuda"])) >= 2, outs

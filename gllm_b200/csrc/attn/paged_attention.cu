@@ -32,6 +32,9 @@ struct AttnParams {
   int max_blocks, Hq, Hkv, G, GP, page_size, num_splits;
   int seq_offset;  // first sequence index handled by this launch
   float scale_log2;
+  // decode with num_splits > 1: arrival counter per (sequence, head group); the LAST split CTA to finish merges
+  // the partial results itself (no separate merge launch). Zero at rest, re-armed by the merging CTA.
+  uint32_t* split_cnt;
 };
 
 template <int D>
@@ -280,6 +283,42 @@ attn_decode_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_cons
       // log2-domain LSE of this split
       p.part_lse[((size_t)seq * p.Hq + head) * p.num_splits + split] =
           (l_all > 0.f) ? (m_all + log2f(l_all)) : -INFINITY;
+    }
+  }
+  if (p.num_splits > 1 && p.split_cnt != nullptr) {
+    // ---------------- last-arriver merge of the KV splits ----------------
+    __shared__ uint32_t s_last;
+    __threadfence();
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    if (tid == 0) {
+      uint32_t* cnt = p.split_cnt + (size_t)seq * gridDim.x + blockIdx.x;
+      const uint32_t old = atomicAdd(cnt, 1u);
+      s_last = (old == (uint32_t)p.num_splits - 1u) ? 1u : 0u;
+      if (s_last) *cnt = 0u;
+    }
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    if (s_last && row < p.GP) {
+      __threadfence();
+      const int head = hbase + row;
+      const size_t sh = (size_t)seq * p.Hq + head;
+      float m = -INFINITY;
+      for (int sp = 0; sp < p.num_splits; ++sp) m = fmaxf(m, __ldcg(p.part_lse + sh * p.num_splits + sp));
+      float den = 0.f;
+      for (int sp = 0; sp < p.num_splits; ++sp) {
+        const float l = __ldcg(p.part_lse + sh * p.num_splits + sp);
+        den += (l == -INFINITY) ? 0.f : exp2f(l - m);
+      }
+      const float inv = den > 0.f ? 1.f / den : 0.f;
+      for (int c = (tid & 7) * 4; c < D; c += 32) {
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int sp = 0; sp < p.num_splits; ++sp) {
+          const float l = __ldcg(p.part_lse + sh * p.num_splits + sp);
+          const float w = (l == -INFINITY) ? 0.f : exp2f(l - m) * inv;
+          const float4 v = __ldcg(reinterpret_cast<const float4*>(p.part_o + (sh * p.num_splits + sp) * D + c));
+          acc.x += w * v.x; acc.y += w * v.y; acc.z += w * v.z; acc.w += w * v.w;
+        }
+        *reinterpret_cast<uint2*>(p.out + sh * D + c) = make_uint2(pack_bf16(acc.x, acc.y), pack_bf16(acc.z, acc.w));
+      }
     }
   }
 }
@@ -543,7 +582,7 @@ using namespace b200;
 GLLM_EXPORT int gllm_attn_decode(const void* q, int64_t q_ts, void* out, const void* k_cache, const void* v_cache,
                                  int64_t num_pages, const void* block_table, const void* seq_lens, void* part_o,
                                  void* part_lse, int num_seqs, int seq_offset, int max_blocks, int Hq, int Hkv,
-                                 int D, int page_size, int num_splits, float scale, void* stream) {
+                                 int D, int page_size, int num_splits, float scale, void* split_cnt, void* stream) {
   if (num_seqs <= 0) return 0;
   if (page_size < 8 || kTileN % page_size != 0 || Hq % Hkv != 0) {
     fprintf(stderr, "[gllm_b200] attn_decode: unsupported page_size=%d / heads\n", page_size);
@@ -565,6 +604,7 @@ GLLM_EXPORT int gllm_attn_decode(const void* q, int64_t q_ts, void* out, const v
   p.page_size = page_size; p.num_splits = num_splits < 1 ? 1 : num_splits;
   p.seq_offset = seq_offset;
   p.scale_log2 = scale * 1.4426950408889634f;
+  p.split_cnt = reinterpret_cast<uint32_t*>(split_cnt);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   int rc;
   switch (D) {
@@ -576,7 +616,7 @@ GLLM_EXPORT int gllm_attn_decode(const void* q, int64_t q_ts, void* out, const v
       return 1;
   }
   if (rc) return rc;
-  if (p.num_splits > 1) {
+  if (p.num_splits > 1 && p.split_cnt == nullptr) {
     // merge covers sequences [seq_offset, seq_offset + num_seqs)
     const size_t off = (size_t)seq_offset * Hq;
     CUDA_CHECK_RET(launch_pdl(attn_merge_kernel, dim3(num_seqs * Hq), dim3(D < 128 ? D : 128), 0, st,

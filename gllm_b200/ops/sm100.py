@@ -224,6 +224,7 @@ def rope_kv_write(q: torch.Tensor, k: torch.Tensor, v: Optional[torch.Tensor], p
 # paged attention
 # ----------------------------------------------------------------------------------------------
 _attn_ws = {}
+_FUSED_MERGE = os.environ.get("GLLM_ATTN_FUSED_MERGE", "0") == "1"
 
 
 def decode_splits(num_seqs: int, num_kv_heads: int, num_q_heads: int, max_seq_len: int) -> int:
@@ -245,10 +246,21 @@ def _workspace(device, n_floats: int, tag: str) -> torch.Tensor:
     return ws
 
 
+def _split_counters(device, n: int) -> torch.Tensor:
+    """Zero-at-rest arrival counters of the split-KV decode kernel (the last split CTA merges in-kernel)."""
+    key = (device, "split_cnt")
+    c = _attn_ws.get(key)
+    if c is None or c.numel() < n:
+        c = torch.zeros(max(n, 1 << 16), dtype=torch.int32, device=device)
+        _attn_ws[key] = c
+    return c
+
+
 def reserve_attn_workspace(device, max_seqs: int, num_q_heads: int, head_dim: int, max_splits: int = 16):
     """Pre-size the split-KV workspace (call before CUDA-graph capture so pointers stay fixed)."""
     _workspace(device, max_seqs * num_q_heads * max_splits * head_dim, "part_o")
     _workspace(device, max_seqs * num_q_heads * max_splits, "part_lse")
+    _split_counters(device, max_seqs * num_q_heads)
 
 
 def paged_attention(q: torch.Tensor, k_cache: torch.Tensor, v_cache: torch.Tensor, block_table: torch.Tensor,
@@ -272,14 +284,17 @@ def paged_attention(q: torch.Tensor, k_cache: torch.Tensor, v_cache: torch.Tenso
         if splits is None:
             splits = decode_splits(num_decode_seqs, hkv, hq, max_seq_len)
         part_o = part_lse = None
+        split_cnt = None
         if splits > 1:
             part_o = _workspace(q.device, num_decode_seqs * hq * splits * d, "part_o")
             part_lse = _workspace(q.device, num_decode_seqs * hq * splits, "part_lse")
+            if _FUSED_MERGE:   # last split CTA merges in-kernel; measured 4 % slower end to end than the
+                split_cnt = _split_counters(q.device, num_decode_seqs * hq)   # PDL-launched merge kernel
         rc = L.gllm_attn_decode(_p(q), q.stride(0), _p(out), _p(k_cache), _p(v_cache), pages, _p(block_table),
                                 _p(seq_lens), _p(part_o), _p(part_lse), num_decode_seqs, 0, max_blocks, hq, hkv, d,
-                                page_size, splits, float(scale), st)
+                                page_size, splits, float(scale), _p(split_cnt), st)
         check(rc, "attn_decode")
-        _count(2 if splits > 1 else 1)
+        _count(1 if (splits == 1 or split_cnt is not None) else 2)
     n_prefill = num_seqs - num_decode_seqs
     if n_prefill > 0:
         assert query_start_loc.dtype == torch.int32

@@ -74,13 +74,14 @@ class Comm:
         self.tok_in = self.tok_out = None
 
     # addresses ---------------------------------------------------------------------------------
-    def _addr(self, name: str, idx: int = 0) -> str:
+    def _addr(self, name: str, idx: int = 0, bind: bool = False) -> str:
         if self.tcp_host is not None:
-            # multi-node: deterministic port per channel (reference: zmq_port_base + rank)
+            # multi-node: deterministic port per channel (reference: zmq_port_base + rank). Every TCP endpoint is
+            # BOUND on the master node (front-end / driver) and connected to from wherever the other side runs,
+            # so no node needs to know a slave's address.
             table = {"fe_req": 0, "fe_out": 1, "tok": 2}
             port = self.port_base + (table[name] if name in table else 3 + idx)
-            host = self.master_addr if name in table else "*"
-            return f"tcp://{host}:{port}"
+            return f"tcp://{'*' if bind else self.master_addr}:{port}"
         return f"{self.base}_{name}_{idx}"
 
     def init(self):
@@ -88,27 +89,22 @@ class Comm:
         self.ctx = zmq.Context.instance()
         if self.frontend:
             self.sock_fe_out = make_socket(self.ctx, P, self._addr("fe_req"), bind=False)
-            self.sock_fe_in = make_socket(self.ctx, L, self._addr("fe_out"), bind=True)
+            self.sock_fe_in = make_socket(self.ctx, L, self._addr("fe_out", bind=True), bind=True)
             return self
+        tcp = self.tcp_host is not None
         if self.rank == 0:
-            self.sock_fe_in = make_socket(self.ctx, L, self._addr("fe_req"), bind=True)
+            self.sock_fe_in = make_socket(self.ctx, L, self._addr("fe_req", bind=True), bind=True)
             self.sock_fe_out = make_socket(self.ctx, P, self._addr("fe_out"), bind=False)
             for r in range(1, self.world_size):
-                self.batch_out.append(make_socket(self.ctx, P, self._peer_addr(r, connect=True), bind=False))
+                # ipc: the peer binds its inbox and the driver connects; tcp: the driver binds, the peer connects
+                self.batch_out.append(make_socket(self.ctx, P, self._addr("batch", r, bind=tcp), bind=tcp))
             if self.output_rank != 0:
-                self.tok_in = make_socket(self.ctx, L, self._addr("tok"), bind=True)
+                self.tok_in = make_socket(self.ctx, L, self._addr("tok", bind=True), bind=True)
         else:
-            self.batch_in = make_socket(self.ctx, L, self._peer_addr(self.rank, connect=False), bind=True)
+            self.batch_in = make_socket(self.ctx, L, self._addr("batch", self.rank, bind=not tcp), bind=not tcp)
             if self.rank == self.output_rank:
-                addr = self._addr("tok")
-                self.tok_out = make_socket(self.ctx, P, addr.replace("*", self.master_addr), bind=False)
+                self.tok_out = make_socket(self.ctx, P, self._addr("tok"), bind=False)
         return self
-
-    def _peer_addr(self, r: int, connect: bool) -> str:
-        if self.tcp_host is not None:
-            host = self.peer_hosts[r] if connect and getattr(self, "peer_hosts", None) else "*"
-            return f"tcp://{host}:{self.port_base + 3 + r}"
-        return f"{self.base}_batch_{r}"
 
     # front-end <-> driver ----------------------------------------------------------------------
     def send_frontend(self, pkg: IPCPackage):

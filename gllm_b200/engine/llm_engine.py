@@ -433,11 +433,11 @@ class _NoFrontend:
         c.ctx = zmq.Context.instance()
         if c.rank == 0:
             for r in range(1, c.world_size):
-                c.batch_out.append(make_socket(c.ctx, P, c._peer_addr(r, connect=True), bind=False))
+                c.batch_out.append(make_socket(c.ctx, P, c._addr("batch", r), bind=False))
             if c.output_rank != 0:
                 c.tok_in = make_socket(c.ctx, L, c._addr("tok"), bind=True)
         else:
-            c.batch_in = make_socket(c.ctx, L, c._peer_addr(c.rank, connect=False), bind=True)
+            c.batch_in = make_socket(c.ctx, L, c._addr("batch", c.rank), bind=True)
             if c.rank == c.output_rank:
                 c.tok_out = make_socket(c.ctx, P, c._addr("tok"), bind=False)
         return self

@@ -90,3 +90,49 @@ def test_server_subprocess_with_serving_benchmark():
             srv.wait(timeout=10)
         except Exception:  # noqa: BLE001
             srv.kill()
+
+
+def test_master_slave_two_node_launch_on_localhost():
+    """`--launch-mode master|slave`: two "nodes" (one worker rank each, PP=2) talk over TCP ZeroMQ + gloo; every
+    TCP endpoint is bound on the master node, the slave only needs the master address
+    (reference: api_server.py:312-322, comm.py)."""
+    mp_, zp = _free_port(), _free_port()
+    common = f"""
+import sys
+sys.path.insert(0, {ROOT!r})
+from gllm_b200 import LLM
+from gllm_b200.models.presets import tiny
+cfg = tiny("Qwen3ForCausalLM", num_hidden_layers=4)
+kw = dict(load_format="dummy", pp_size=2, tp_size=1, maxp=48, maxd=16, num_cpu_pages=128, model_max_length=256,
+          log_stats=False, device="cpu", master_addr="127.0.0.1", master_port={mp_}, zmq_port_base={zp},
+          host="127.0.0.1")
+"""
+    slave = common + """
+if __name__ == "__main__":
+    llm = LLM(cfg, launch_mode="slave", worker_ranks=[1], **kw)
+    for p in llm.procs:
+        p.join()
+"""
+    master = common + """
+if __name__ == "__main__":
+    llm = LLM(cfg, launch_mode="master", worker_ranks=[0], **kw)
+    outs = llm.generate(tokens=[[5, 17, 99], [9] * 40], output_lens=[6, 7], ignore_eos=True)
+    assert [len(s.token_ids) - s.prompt_len for s in outs] == [6, 7]
+    print("MULTINODE_OK")
+    llm.shutdown()
+"""
+    fs, fm = tempfile.mktemp(suffix="_s.py"), tempfile.mktemp(suffix="_m.py")
+    open(fs, "w").write(slave)
+    open(fm, "w").write(master)
+    env = dict(os.environ, GLLM_B200_LOG="WARNING")
+    ps = subprocess.Popen([sys.executable, fs], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    try:
+        time.sleep(1.0)
+        pm = subprocess.run([sys.executable, fm], env=env, capture_output=True, text=True, timeout=240)
+        assert "MULTINODE_OK" in pm.stdout, pm.stdout[-1500:] + pm.stderr[-2500:]
+    finally:
+        ps.terminate()
+        try:
+            ps.wait(timeout=10)
+        except Exception:  # noqa: BLE001
+            ps.kill()

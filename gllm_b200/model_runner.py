@@ -11,6 +11,7 @@ copy issued asynchronously), or the (hidden, residual) views to ship to the next
 """
 from __future__ import annotations
 
+import os
 import time
 from dataclasses import dataclass
 from typing import Dict, List, Optional
@@ -100,6 +101,8 @@ class ModelRunner:
         self.input_data = InputData(self.max_num_batched_tokens, max(self.max_running_seqs, 1), max_blocks,
                                     self.device, mrope=mrope)
         self.input_data.need_tok_seq = bool(self.loader.use_mla)
+        # vocab-parallel sampling: the forward (and its CUDA graphs) ends at this rank's logits shard
+        self.vp_sample = cfg.tp_size > 1 and os.environ.get("GLLM_VP_SAMPLE", "1") != "0"
         h, dt = self.spec.hidden_size, self.spec.dtype
         if not ps.is_first_pp_rank():
             self.input_hidden = torch.zeros(self.max_num_batched_tokens, h, dtype=dt, device=self.device)
@@ -172,7 +175,7 @@ class ModelRunner:
         else:
             h, r = self.model(inp, kv, self.tpc, hidden, residual)
         if ps.is_last_pp_rank():
-            return self.model.compute_logits(inp, h, self.tpc, all_rows=all_rows), None
+            return self.model.compute_logits(inp, h, self.tpc, all_rows=all_rows, local=self.vp_sample), None
         return h, r
 
     def capture_graphs(self):
@@ -281,6 +284,10 @@ class ModelRunner:
         e = logits.shape[0]
         if e == 0:
             return StepResult(tokens=self.tokens_out[:0], num_emit=0)
+        if self.vp_sample:
+            if batch.all_greedy and not batch.need_penalty:
+                return self._finish_sample(self._vp_greedy(logits), e)
+            logits = self.tpc.gather_logits(logits, self.spec.vocab_size)
         seen = None
         if batch.need_penalty:
             seen = self._seen_bits()
@@ -301,6 +308,37 @@ class ModelRunner:
         if not batch.all_greedy:
             self.step_counter += 1
         toks = Fn.sample(logits, inp, seen, seed=self.cfg.seed, step=self.step_counter)
+        return self._finish_sample(toks, e)
+
+    def _vp_greedy(self, shard: torch.Tensor) -> torch.Tensor:
+        """Vocab-parallel greedy sampling: every rank takes the argmax of its own vocab shard
+        with the sampler kernel, the ranks exchange (value, global index) pairs — 8 bytes per row instead of the
+        [E, V] logits — and pick the winner (lowest rank on ties == lowest token id)."""
+        import torch.distributed as dist
+        e, per = shard.shape
+        st = ps.get_state()
+        r0 = st.tp_rank * per
+        valid = max(0, min(per, self.spec.vocab_size - r0))   # the last rank's shard ends with padding rows
+        pack = torch.empty(e, 2, dtype=torch.float32, device=shard.device)
+        if valid > 0:
+            if shard.is_cuda:
+                from gllm_b200.ops import sm100
+                val = torch.empty(e, dtype=torch.float32, device=shard.device)
+                idx = sm100.sample(shard[:, :valid], out_max=val, vocab_offset=r0)
+            else:
+                val, idx = shard[:, :valid].float().max(dim=1)
+                idx = idx + r0
+            pack[:, 0] = val
+            pack[:, 1] = idx.float()   # token ids < 2^24 are exact in fp32
+        else:
+            pack[:, 0] = float("-inf")
+            pack[:, 1] = 0
+        allp = torch.empty(st.tp_size, e, 2, dtype=torch.float32, device=shard.device)
+        dist.all_gather_into_tensor(allp.view(st.tp_size * e, 2), pack, group=st.tp_group)
+        best = allp[:, :, 0].argmax(dim=0, keepdim=True)
+        return allp[:, :, 1].gather(0, best)[0].to(torch.int32)
+
+    def _finish_sample(self, toks: torch.Tensor, e: int) -> StepResult:
         self.tokens_out[:e].copy_(toks)
         res = StepResult(tokens=self.tokens_out, num_emit=e)
         if self.device.type == "cuda":

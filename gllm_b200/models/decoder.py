@@ -357,12 +357,16 @@ class CausalLM(nn.Module):
                 h, residual = layer(inp, h, residual, kv_cache, tpc, nxt)
         return h, residual
 
-    def compute_logits(self, inp, hidden: torch.Tensor, tpc: TPComm, all_rows: bool = False) -> torch.Tensor:
-        """Logits of the last token of every emitting sequence -> [E, V]."""
+    def compute_logits(self, inp, hidden: torch.Tensor, tpc: TPComm, all_rows: bool = False,
+                       local: bool = False) -> torch.Tensor:
+        """Logits of the last token of every emitting sequence -> [E, V]; `local=True` returns this rank's vocab
+        shard [E, Vp/tp] instead (vocab-parallel sampling: the runner reduces winners, not logits)."""
         hidden = tpc.materialize(hidden)
         rows = hidden if all_rows else Fn.gather_rows(hidden, inp.logits_idx)
-        local = Fn.linear(rows, self.lm_head_w)
-        return tpc.gather_logits(local, self.spec.vocab_size)
+        shard = Fn.linear(rows, self.lm_head_w)
+        if local:
+            return shard
+        return tpc.gather_logits(shard, self.spec.vocab_size)
 
     # -- weights ----------------------------------------------------------------------------------
     def process_weights(self):

@@ -157,7 +157,8 @@ class Worker(ProfilerMixin):
             did = True
             self.batch_counter += 1
             batch = build_batch(entries, self.cfg.page_size, self.runner.spec.vocab_size, self.batch_counter,
-                                mrope=self.runner.input_data.mrope)
+                                mrope=self.runner.input_data.mrope, prev=getattr(self, "_last_batch", None))
+            self._last_batch = batch if self.cfg.pp_size == 1 else None   # PP interleaves micro-batches
             if self.comm is not None:
                 self.comm.send_batch(batch)
             res = self.runner.step(batch)

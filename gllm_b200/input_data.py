@@ -45,6 +45,8 @@ class BatchArrays:
     clear_slots: Optional[np.ndarray] = None  # int32: bitmask rows to zero first (slot re-use)
     batch_id: int = 0
     mm: Optional[dict] = None  # multimodal payload (pixel values, grids) for the first stage
+    seq_ids: Optional[list] = None  # driver-local: sequence id per row (incremental decode batches); not sent
+    seq_index: Optional[dict] = None  # driver-local: seq id -> row (built lazily by the next batch)
 
     def is_decode_only(self) -> bool:
         return self.num_decode_seqs == self.num_seqs
@@ -88,9 +90,62 @@ def _page_array(seq) -> np.ndarray:
     return pt
 
 
-def build_batch(entries, page_size: int, vocab_size: int, batch_id: int = 0, mrope: bool = False) -> BatchArrays:
-    """entries: List[ScheduledSeq], decode entries first (scheduler invariant)."""
+def _build_decode_fast(entries, page_size: int, batch_id: int, prev: "BatchArrays") -> Optional["BatchArrays"]:
+    """Steady-state decode: the same sequences as the previous micro-batch, one new token each. Everything is
+    derived from the previous arrays with vectorised numpy (new arrays, never in place: zero-copy zmq sends may
+    still reference the old ones); only rows that crossed a page boundary touch their Python page table."""
     b = len(entries)
+    if prev is None or prev.seq_ids is None or b != prev.num_seqs or prev.num_decode_seqs != b or prev.need_penalty \
+            or prev.mm is not None or prev.positions.ndim != 1:
+        return None
+    # the scheduler re-queues finished-step sequences head-first, so the row order flips between iterations:
+    # map every entry to its row in the previous batch
+    where = prev.seq_index
+    if where is None:
+        where = {sid: i for i, sid in enumerate(prev.seq_ids)}
+        prev.seq_index = where
+    try:   # one pass over the entries: (previous row, position, token, seq id)
+        data = [(where[e.seq.seq_id], e.start, e.seq.token_ids[e.start], e.seq.seq_id) if e.n == 1 and e.emits
+                else None for e in entries]
+        arr = np.array(data, dtype=np.int64)
+    except (KeyError, TypeError, ValueError):
+        return None
+    if arr.ndim != 2:
+        return None
+    perm = arr[:, 0]
+    starts = arr[:, 1].astype(np.int32)
+    tokens = arr[:, 2].astype(np.int32)
+    ids = arr[:, 3].tolist()
+    if not np.array_equal(starts, prev.positions[perm] + 1):
+        return None
+    blk = starts // page_size
+    bt = prev.block_table[perm]              # fancy indexing: a new array
+    width = int(blk.max()) + 1
+    if width > bt.shape[1]:
+        bt = np.concatenate([bt, np.zeros((b, width - bt.shape[1]), dtype=np.int32)], axis=1)
+    for i in np.nonzero(starts % page_size == 0)[0]:      # first token of a fresh page
+        bt[i, blk[i]] = entries[i].seq.page_table[blk[i]]
+    rows = np.arange(b, dtype=np.int32)
+    slots = bt[rows, blk] * page_size + starts % page_size
+    seq_lens = starts + 1
+    return BatchArrays(
+        tokens=tokens, positions=starts, slot_mapping=slots.astype(np.int32), block_table=bt, seq_lens=seq_lens,
+        query_start_loc=prev.query_start_loc, logits_idx=prev.logits_idx, emit_seq=prev.emit_seq,
+        temperature=prev.temperature[perm], top_k=prev.top_k[perm], top_p=prev.top_p[perm],
+        rep_penalty=prev.rep_penalty[perm], state_slot=prev.state_slot[perm], num_decode_seqs=b, num_seqs=b, num_tokens=b, max_q_len=1,
+        max_seq_len=int(seq_lens.max()), all_greedy=prev.all_greedy, need_penalty=False, batch_id=batch_id,
+        seq_ids=ids)
+
+
+def build_batch(entries, page_size: int, vocab_size: int, batch_id: int = 0, mrope: bool = False,
+                prev: Optional["BatchArrays"] = None) -> BatchArrays:
+    """entries: List[ScheduledSeq], decode entries first (scheduler invariant). `prev` (the previous
+    micro-batch of this engine) enables the incremental decode fast path."""
+    b = len(entries)
+    if prev is not None and not mrope and b:
+        fast = _build_decode_fast(entries, page_size, batch_id, prev)
+        if fast is not None:
+            return fast
     n_dec = 0
     for e in entries:
         if e.is_decode:
@@ -172,7 +227,8 @@ def build_batch(entries, page_size: int, vocab_size: int, batch_id: int = 0, mro
         max_seq_len=int(seq_lens.max()) if b else 0, all_greedy=all_greedy, need_penalty=need_penalty,
         seen_rows=np.concatenate(seen_rows) if seen_rows else None,
         seen_tokens=np.concatenate(seen_tokens) if seen_tokens else None,
-        clear_slots=np.asarray(clear_slots, dtype=np.int32) if clear_slots else None, batch_id=batch_id, mm=mm)
+        clear_slots=np.asarray(clear_slots, dtype=np.int32) if clear_slots else None, batch_id=batch_id, mm=mm,
+        seq_ids=[e.seq.seq_id for e in entries] if n_dec == b else None)
 
 
 class InputData:
@@ -250,11 +306,13 @@ class InputData:
         self._put(self._qsl, batch.query_start_loc)
         if self.num_emit:
             self._put(self._logits_idx, batch.logits_idx)
-            self._put(self._temperature, batch.temperature)
-            self._put(self._top_k, batch.top_k)
-            self._put(self._top_p, batch.top_p)
-            self._put(self._rep_penalty, batch.rep_penalty)
-            self._put(self._state_slot, batch.state_slot)
+            # the greedy argmax path of the sm_100a sampler reads none of these
+            if not (self.device.type == "cuda" and batch.all_greedy and not batch.need_penalty):
+                self._put(self._temperature, batch.temperature)
+                self._put(self._top_k, batch.top_k)
+                self._put(self._top_p, batch.top_p)
+                self._put(self._rep_penalty, batch.rep_penalty)
+                self._put(self._state_slot, batch.state_slot)
 
     def pad_for_graph(self, bucket: int, dummy_slot: int, dummy_page: int):
         """Pad a decode-only batch of B seqs to `bucket` seqs: dummy rows attend to one dummy token

@@ -266,3 +266,44 @@ def test_build_batch_layout_and_wire():
               "temperature", "top_k", "top_p"):
         assert np.array_equal(getattr(bt, f), getattr(back, f)), f
     assert back.batch_id == 3 and back.num_decode_seqs == 1
+
+
+def test_incremental_decode_batch_equals_full_rebuild():
+    """The vectorised decode fast path (batch N+1 derived from batch N, rows possibly permuted, pages crossing a
+    boundary) must produce exactly the arrays of a from-scratch build."""
+    import numpy as np
+    from gllm_b200.input_data import build_batch
+    from gllm_b200.scheduler import ScheduledSeq
+    from gllm_b200.sequence import Sequence
+    rng = np.random.default_rng(0)
+    page = 16
+    seqs = []
+    for i in range(13):
+        n = int(rng.integers(20, 90))
+        s = Sequence(i, rng.integers(3, 200, size=n).tolist(), [1], 500, True, 0.7 if i % 3 else 0.0, 0.9, 5 if i % 3 else 1,
+                     1.0)
+        s.prompt_len = n - 3
+        s.page_table = [int(x) for x in rng.permutation(4000)[: (n + page) // page + 1]]
+        s.slot = i + 1
+        seqs.append(s)
+    order = list(range(len(seqs)))
+    prev = None
+    for step in range(40):
+        order.reverse()                      # the scheduler re-queues head-first: row order flips every step
+        ents = [ScheduledSeq(seqs[j], len(seqs[j].token_ids) - 1, 1) for j in order]
+        for e in ents:                       # make sure the page for the new token exists
+            need = e.start // page + 1
+            while len(e.seq.page_table) < need:
+                e.seq.page_table.append(int(rng.integers(4000, 8000)))
+        fast = build_batch(ents, page, 1000, step, prev=prev)
+        full = build_batch(ents, page, 1000, step)
+        for name in ("tokens", "positions", "slot_mapping", "seq_lens", "query_start_loc", "logits_idx", "emit_seq",
+                     "temperature", "top_k", "top_p", "rep_penalty", "state_slot"):
+            assert np.array_equal(getattr(fast, name), getattr(full, name)), (step, name)
+        w = full.block_table.shape[1]
+        assert np.array_equal(fast.block_table[:, :w], full.block_table)
+        assert (fast.num_seqs, fast.num_decode_seqs, fast.num_tokens, fast.max_seq_len, fast.all_greedy) == \
+               (full.num_seqs, full.num_decode_seqs, full.num_tokens, full.max_seq_len, full.all_greedy)
+        prev = fast
+        for s in seqs:
+            s.token_ids.append(int(rng.integers(3, 200)))

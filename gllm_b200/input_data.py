@@ -52,28 +52,36 @@ class BatchArrays:
         return self.num_decode_seqs == self.num_seqs
 
     def to_wire(self):
-        """(header dict, list of buffers) for zero-copy IPC."""
+        """(header dict, [one contiguous buffer]) for zero-copy IPC: every array is packed into a single blob
+        (16-byte aligned sections) so a batch costs two zmq frames per peer instead of one per array."""
         names = ["tokens", "positions", "slot_mapping", "block_table", "seq_lens", "query_start_loc",
                  "logits_idx", "emit_seq", "temperature", "top_k", "top_p", "rep_penalty", "state_slot"]
         opt = ["seen_rows", "seen_tokens", "clear_slots"]
         hdr = {"scalars": (self.num_decode_seqs, self.num_seqs, self.num_tokens, self.max_q_len,
                            self.max_seq_len, self.all_greedy, self.need_penalty, self.batch_id),
                "arrays": [], "mm": self.mm}
-        bufs = []
+        parts, off = [], 0
         for n in names + opt:
             a = getattr(self, n)
             if a is None:
                 continue
             a = np.ascontiguousarray(a)
-            hdr["arrays"].append((n, a.dtype.str, a.shape))
-            bufs.append(a)
-        return hdr, bufs
+            hdr["arrays"].append((n, a.dtype.str, a.shape, off))
+            parts.append(a)
+            off += (a.nbytes + 15) // 16 * 16
+        blob = np.empty(max(off, 16), dtype=np.uint8)
+        for (_, _, _, o), a in zip(hdr["arrays"], parts):
+            blob[o:o + a.nbytes] = a.reshape(-1).view(np.uint8)
+        return hdr, [blob]
 
     @staticmethod
     def from_wire(hdr, bufs) -> "BatchArrays":
         kw = {}
-        for (n, dt, shape), b in zip(hdr["arrays"], bufs):
-            kw[n] = np.frombuffer(b, dtype=np.dtype(dt)).reshape(shape)
+        blob = np.frombuffer(bufs[0], dtype=np.uint8)
+        for n, dt, shape, off in hdr["arrays"]:
+            dtype = np.dtype(dt)
+            count = int(np.prod(shape)) if len(shape) else 1
+            kw[n] = np.frombuffer(blob, dtype=dtype, count=count, offset=off).reshape(shape)
         s = hdr["scalars"]
         return BatchArrays(**kw, num_decode_seqs=s[0], num_seqs=s[1], num_tokens=s[2], max_q_len=s[3],
                            max_seq_len=s[4], all_greedy=s[5], need_penalty=s[6], batch_id=s[7], mm=hdr.get("mm"))

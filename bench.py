@@ -41,6 +41,8 @@ def parse():
     ap.add_argument("--schedule-method", default="chunked_prefill")
     ap.add_argument("--pp", type=int, default=1)
     ap.add_argument("--seed", type=int, default=0)
+    ap.add_argument("--async-schedule", action="store_true",
+                    help="lookahead decode scheduling (CPU-validated; not yet measured on the GPU)")
     return ap.parse_args()
 
 
@@ -134,7 +136,8 @@ def main():
     llm = LLM(args.model, load_format="dummy", tp_size=tp, pp_size=args.pp, maxp=args.maxp, maxd=args.maxd,
               max_cuda_graph_bs=args.max_cuda_graph_bs, schedule_method=args.schedule_method,
               enable_prefix_caching=False, gpu_memory_util=0.85, model_max_length=2048 + 16,
-              tp_mode=args.tp_mode, log_stats=False, launch_mode="inproc", seed=args.seed)
+              tp_mode=args.tp_mode, log_stats=False, launch_mode="inproc", seed=args.seed,
+              async_schedule=args.async_schedule)
     vocab = llm.loader.config["vocab_size"]
     prompts, out_lens = synth_requests(args.num_prompts, vocab, args.seed)
     total_out = sum(out_lens)
@@ -219,7 +222,8 @@ def main():
                        "global_batch": args.num_prompts, "seq_len": "prompt<=1024, prompt+output<=2048",
                        "input_tokens_per_step": total_in, "output_tokens_per_step": total_out,
                        "parallelism": f"tp{tp}" + (f"pp{args.pp}" if args.pp > 1 else ""), "tp_mode": args.tp_mode,
-                       "schedule_method": args.schedule_method, "maxp": args.maxp, "maxd": args.maxd,
+                       "schedule_method": args.schedule_method, "async_schedule": bool(args.async_schedule),
+                       "maxp": args.maxp, "maxd": args.maxd,
                        "l2": "inputs larger than L2 (16 GB of weights + multi-GB KV streamed every iteration)",
                        "engine_iterations_per_step": eng_steps // max(args.steps, 1),
                        "cuda_graph_iterations": (stats1["graph_steps"] - stats0["graph_steps"]) // max(args.steps, 1),

@@ -131,8 +131,8 @@ class AsyncLLM(LLM):
                 if delta:
                     st.put(delta)
             else:
-                st.put(" ".join(str(t) for t in seq.token_ids[seq.cur_length:]) + " ")
-                seq.cur_length = len(seq.token_ids)
+                st.put(" ".join(str(t) for t in seq.token_ids[seq.cur_length:seq.known_len]) + " ")
+                seq.cur_length = seq.known_len
         self._pending_tokens = []
         for seq in self.finished:
             st = self.async_streams.pop(seq.seq_id, None)

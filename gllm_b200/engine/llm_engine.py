@@ -52,7 +52,8 @@ class LLM:
     def __init__(self, model_path, host=None, master_addr="127.0.0.1", master_port=8001, zmq_port_base=8002,
                  launch_mode="normal", worker_ranks=None, load_format="auto", gpu_memory_util=0.9, page_size=16,
                  maxd=2048, maxp=2048, minp=32, iterp=8, kvthresh=0.05, enable_prefix_caching=True, pp_size=1,
-                 tp_size=1, use_ep=True, assigned_layers=None, use_async_worker=False, use_thinking=True,
+                 tp_size=1, use_ep=True, assigned_layers=None, use_async_worker=False, async_schedule=False,
+                 use_thinking=True,
                  schedule_method="chunked_prefill", disable_cuda_graph=False, max_cuda_graph_bs=32,
                  model_max_length=None, mm_processor_min_pixels=None, mm_processor_max_pixels=None, **extra):
         if isinstance(assigned_layers, str):
@@ -65,7 +66,8 @@ class LLM:
             worker_ranks=worker_ranks, gpu_memory_util=gpu_memory_util, page_size=page_size, maxd=maxd, maxp=maxp,
             minp=minp, iterp=iterp, kvthresh=kvthresh, enable_prefix_caching=enable_prefix_caching,
             pp_size=pp_size, tp_size=tp_size, use_ep=use_ep, assigned_layers=assigned_layers,
-            use_async_worker=use_async_worker, use_thinking=use_thinking, schedule_method=schedule_method,
+            use_async_worker=use_async_worker, async_schedule=async_schedule, use_thinking=use_thinking,
+            schedule_method=schedule_method,
             disable_cuda_graph=disable_cuda_graph, max_cuda_graph_bs=max_cuda_graph_bs,
             model_max_length=model_max_length, mm_processor_min_pixels=mm_processor_min_pixels,
             mm_processor_max_pixels=mm_processor_max_pixels, **extra)

@@ -136,8 +136,16 @@ class Worker(ProfilerMixin):
             for batch_id, toks in self.comm.recv_tokens():
                 sch.add_next_tokens(toks)
                 did = True
+        if self.cfg.async_schedule and len(self.pending) == 1:
+            # async scheduling: queue the NEXT decode step behind the one still running on the GPU, before its
+            # tokens are back (the runner feeds them device-side); falls through when the conditions do not hold
+            look = sch.schedule_lookahead()
+            if look:
+                did = True
+                self._launch(look)
+        keep = 1 if (self.cfg.async_schedule and len(self.pending) == 2) else 0   # the step queued just now
         # tokens of our own finished micro-batches
-        while self.pending:
+        while len(self.pending) > keep:
             bid, res = self.pending[0]
             if res.event is not None and not res.event.query():
                 break
@@ -155,19 +163,28 @@ class Worker(ProfilerMixin):
         entries = sch.schedule_once()
         if entries:
             did = True
-            self.batch_counter += 1
-            batch = build_batch(entries, self.cfg.page_size, self.runner.spec.vocab_size, self.batch_counter,
-                                mrope=self.runner.input_data.mrope, prev=getattr(self, "_last_batch", None))
-            self._last_batch = batch if self.cfg.pp_size == 1 else None   # PP interleaves micro-batches
-            if self.comm is not None:
-                self.comm.send_batch(batch)
-            res = self.runner.step(batch)
-            if ps.is_last_pp_rank():
-                if ps.is_output_rank():
-                    self.pending.append((batch.batch_id, res))
-            else:
-                self._pp_send(res)
+            self._launch(entries)
         return did
+
+    def _launch(self, entries):
+        self.batch_counter += 1
+        batch = build_batch(entries, self.cfg.page_size, self.runner.spec.vocab_size, self.batch_counter,
+                            mrope=self.runner.input_data.mrope, prev=getattr(self, "_last_batch", None))
+        if batch.feed_src is None and any(e.seq.pending == e.start for e in entries):
+            # lookahead batch that missed the incremental path: map rows to the previous step's sampler output
+            prev = self._last_batch
+            where = {sid: i for i, sid in enumerate(prev.seq_ids)}
+            import numpy as np
+            batch.feed_src = np.asarray([where[e.seq.seq_id] for e in entries], dtype=np.int32)
+        self._last_batch = batch if self.cfg.pp_size == 1 else None   # PP interleaves micro-batches
+        if self.comm is not None:
+            self.comm.send_batch(batch)
+        res = self.runner.step(batch)
+        if ps.is_last_pp_rank():
+            if ps.is_output_rank():
+                self.pending.append((batch.batch_id, res))
+        else:
+            self._pp_send(res)
 
     def _free_finished_slots(self, out: SchedulerOutput):
         for sid in out.free_ids:

@@ -232,6 +232,8 @@ def make_parser() -> argparse.ArgumentParser:
     p.add_argument("--disable-thinking", action="store_true")
     p.add_argument("--model-max-length", type=int, default=None)
     p.add_argument("--use-async-worker", action="store_true")
+    p.add_argument("--async-schedule", action="store_true",
+                   help="queue the next decode step before the previous step's tokens are back on the host")
     p.add_argument("--gpu-memory-util", type=float, default=0.9)
     p.add_argument("--enable-prefix-caching", action="store_true")
     p.add_argument("--page-size", type=int, default=16)
@@ -263,7 +265,8 @@ def engine_kwargs(args) -> dict:
                 page_size=args.page_size, maxd=args.maxd, maxp=args.maxp, minp=args.minp, iterp=args.iterp,
                 kvthresh=args.kvthresh, enable_prefix_caching=args.enable_prefix_caching, pp_size=args.pp,
                 tp_size=args.tp, use_ep=not args.disable_ep, assigned_layers=args.assigned_layers,
-                use_async_worker=args.use_async_worker, use_thinking=not args.disable_thinking,
+                use_async_worker=args.use_async_worker, async_schedule=args.async_schedule,
+                use_thinking=not args.disable_thinking,
                 schedule_method=args.schedule_method, disable_cuda_graph=args.disable_cuda_graph,
                 max_cuda_graph_bs=args.max_cuda_graph_bs, model_max_length=args.model_max_length,
                 mm_processor_min_pixels=args.mm_processor_min_pixels,

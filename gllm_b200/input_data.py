@@ -45,6 +45,9 @@ class BatchArrays:
     clear_slots: Optional[np.ndarray] = None  # int32: bitmask rows to zero first (slot re-use)
     batch_id: int = 0
     mm: Optional[dict] = None  # multimodal payload (pixel values, grids) for the first stage
+    # lookahead (async scheduling): row i takes its input token from element feed_src[i] of the PREVIOUS step's
+    # device-side sampler output instead of `tokens[i]` (which holds a placeholder)
+    feed_src: Optional[np.ndarray] = None
     seq_ids: Optional[list] = None  # driver-local: sequence id per row (incremental decode batches); not sent
     seq_index: Optional[dict] = None  # driver-local: seq id -> row (built lazily by the next batch)
 
@@ -56,7 +59,7 @@ class BatchArrays:
         (16-byte aligned sections) so a batch costs two zmq frames per peer instead of one per array."""
         names = ["tokens", "positions", "slot_mapping", "block_table", "seq_lens", "query_start_loc",
                  "logits_idx", "emit_seq", "temperature", "top_k", "top_p", "rep_penalty", "state_slot"]
-        opt = ["seen_rows", "seen_tokens", "clear_slots"]
+        opt = ["seen_rows", "seen_tokens", "clear_slots", "feed_src"]
         hdr = {"scalars": (self.num_decode_seqs, self.num_seqs, self.num_tokens, self.max_q_len,
                            self.max_seq_len, self.all_greedy, self.need_penalty, self.batch_id),
                "arrays": [], "mm": self.mm}
@@ -136,7 +139,8 @@ def _build_decode_fast(entries, page_size: int, batch_id: int, prev: "BatchArray
     rows = np.arange(b, dtype=np.int32)
     slots = bt[rows, blk] * page_size + starts % page_size
     seq_lens = starts + 1
-    return BatchArrays(
+    feed = perm.astype(np.int32) if (tokens < 0).any() else None   # lookahead rows: token still on the device
+    return BatchArrays(feed_src=feed,
         tokens=tokens, positions=starts, slot_mapping=slots.astype(np.int32), block_table=bt, seq_lens=seq_lens,
         query_start_loc=prev.query_start_loc, logits_idx=prev.logits_idx, emit_seq=prev.emit_seq,
         temperature=prev.temperature[perm], top_k=prev.top_k[perm], top_p=prev.top_p[perm],
@@ -269,6 +273,7 @@ class InputData:
         self._rep_penalty = buf((max_seqs,), f32)
         self._state_slot = buf((max_seqs,), i32)
         self._tok_seq = buf((max_tokens,), i32)
+        self._feed = buf((max_seqs,), i32)
         self.need_tok_seq = False  # MLA attention wants token -> sequence for mixed / prefill batches
         self.batch: Optional[BatchArrays] = None
         self.num_tokens = self.num_seqs = self.num_decode_seqs = self.num_emit = 0
@@ -309,6 +314,8 @@ class InputData:
         if self.need_tok_seq and not batch.is_decode_only():
             qsl = batch.query_start_loc
             self._put(self._tok_seq, np.repeat(np.arange(batch.num_seqs, dtype=np.int32), np.diff(qsl)))
+        if batch.feed_src is not None:
+            self._put(self._feed, batch.feed_src)
         self._put(self._block_table, batch.block_table)
         self._put(self._seq_lens, batch.seq_lens)
         self._put(self._qsl, batch.query_start_loc)
@@ -321,6 +328,13 @@ class InputData:
                 self._put(self._top_p, batch.top_p)
                 self._put(self._rep_penalty, batch.rep_penalty)
                 self._put(self._state_slot, batch.state_slot)
+
+    def apply_feed(self, prev_tokens_out: torch.Tensor):
+        """Lookahead step: the input tokens are the previous step's sampled tokens, still on the device."""
+        b = self.batch.feed_src.shape[0]
+        idx = self._feed[1][:b]
+        self._tokens[1][:b].copy_(prev_tokens_out.index_select(0, idx.long() if prev_tokens_out.device.type == "cpu"
+                                                               else idx))
 
     def pad_for_graph(self, bucket: int, dummy_slot: int, dummy_page: int):
         """Pad a decode-only batch of B seqs to `bucket` seqs: dummy rows attend to one dummy token

@@ -110,7 +110,12 @@ class ModelRunner:
         if ps.is_last_pp_rank():
             pin = is_cuda
             self.tokens_out = torch.zeros(max(self.max_running_seqs, 1), dtype=torch.int32, device=self.device)
-            self.tokens_host = torch.zeros(max(self.max_running_seqs, 1), dtype=torch.int32, pin_memory=pin)
+            # two pinned result buffers: with async scheduling the next step's D2H copy may land before the host
+            # has read the previous step's tokens
+            self._tokens_host2 = [torch.zeros(max(self.max_running_seqs, 1), dtype=torch.int32, pin_memory=pin)
+                                  for _ in range(2)]
+            self._host_flip = 0
+            self.tokens_host = self._tokens_host2[0]
             self.step_counter = torch.zeros(1, dtype=torch.int64, device=self.device)
         logger.info("model loaded in %.1fs", time.time() - t0)
         self.profile_run()
@@ -235,6 +240,8 @@ class ModelRunner:
         if self.graphs and batch.is_decode_only() and batch.num_seqs <= self.capture_sizes[0]:
             bucket = min(b for b in self.graphs if b >= batch.num_seqs)
         inp.load(batch)
+        if batch.feed_src is not None:
+            inp.apply_feed(self.tokens_out)
         self.stats["h2d_bytes"] += inp.h2d_bytes()
         if self.time_steps and self.device.type == "cuda":
             ev0 = torch.cuda.Event(enable_timing=True)
@@ -340,8 +347,13 @@ class ModelRunner:
 
     def _finish_sample(self, toks: torch.Tensor, e: int) -> StepResult:
         self.tokens_out[:e].copy_(toks)
-        res = StepResult(tokens=self.tokens_out, num_emit=e)
+        # (CPU: no async D2H copy — snapshot the values, a lookahead step may overwrite tokens_out before the
+        # scheduler reads them)
+        res = StepResult(tokens=self.tokens_out if self.device.type == "cuda" else self.tokens_out[:e].clone(),
+                         num_emit=e)
         if self.device.type == "cuda":
+            self._host_flip ^= 1
+            self.tokens_host = self._tokens_host2[self._host_flip]
             self.tokens_host[:e].copy_(self.tokens_out[:e], non_blocking=True)
             self.stats["d2h_bytes"] += 4 * e
             ev = torch.cuda.Event()

@@ -59,6 +59,9 @@ def throttled_prefill_budget(headroom_tokens: int, world_size: int, free_ratio: 
     return budget
 
 
+PLACEHOLDER = -1  # token id of a position whose value is still being sampled on the device (lookahead step)
+
+
 class ScheduledSeq:
     """One entry of a micro-batch: compute tokens [start, start + n) of `seq`."""
     __slots__ = ("seq", "start", "n", "emits", "is_decode")
@@ -144,10 +147,21 @@ class Scheduler:
             seq = ent.seq
             if ent.emits:
                 k += 1
+            if seq.zombie:
+                # finished (or aborted) while this lookahead step was already in flight: its token is
+                # discarded, its pages can go now unless yet another step still references them
+                if not self._in_flight(seq):
+                    seq.zombie = False
+                    if seq.page_table:
+                        self.mm.free(seq)
+                continue
             if seq.is_abort:
                 if seq.page_table:
-                    self.mm.free(seq)
                     out.free_ids.append(seq.seq_id)
+                    if self._in_flight(seq):
+                        seq.zombie = True
+                    else:
+                        self.mm.free(seq)
                 self.abort_ids.discard(seq.seq_id)
                 continue
             seq.computed_token_num = max(seq.computed_token_num, ent.start + ent.n)
@@ -155,14 +169,63 @@ class Scheduler:
                 tok = int(next_tokens[k - 1])
                 out.act_schedule_ids.append(seq.seq_id)
                 out.next_tokens.append(tok)
-                seq.append(tok)
+                ahead = seq.pending == ent.start + ent.n   # a lookahead step already follows this one
+                if ahead:
+                    seq.token_ids[seq.pending] = tok
+                    seq.pending = -1
+                else:
+                    seq.append(tok)
                 if seq.is_finish:
                     out.free_ids.append(seq.seq_id)
-                    self.mm.free(seq)
-                else:
+                    if ahead:
+                        seq.zombie = True
+                    else:
+                        self.mm.free(seq)
+                elif not ahead:
                     self.seqs_to_decode.appendleft(seq)
             # else: unfinished prefill — its continuation is already at the head of seqs_to_prefill
         return out
+
+    def _in_flight(self, seq: Sequence) -> bool:
+        return any(e.seq is seq for b in self.batch_running for e in b)
+
+    def schedule_lookahead(self) -> Optional[List["ScheduledSeq"]]:
+        """Asynchronous scheduling: while the single in-flight decode batch is still running, schedule the decode
+        step that follows it. The input token of every row is not known on the host yet — the sequence gets a
+        PLACEHOLDER and the runner feeds the value from the previous step's device-side sampler output — so the
+        GPU never waits for the host's output processing / scheduling / batch building. Returns None whenever the
+        steady-state assumptions do not hold (pending prefills, prefix caching, penalties, no KV headroom, ...),
+        in which case the caller simply waits for the in-flight batch as before."""
+        if self.pp_size != 1 or len(self.batch_running) != 1 or self.seqs_to_prefill or self.seqs_to_decode or \
+                self.next_tokens_queue or self.abort_ids or isinstance(self.mm, PrefixMemoryManager):
+            return None
+        base = self.batch_running[0]
+        cont = []
+        ps = self.page_size
+        need = 0
+        for ent in base:
+            seq = ent.seq
+            if not ent.is_decode or seq.pending >= 0 or seq.repetition_penalty != 1.0 or seq.mm_state:
+                return None
+            if seq.is_abort or seq.zombie:
+                continue
+            if len(seq.token_ids) + 1 - seq.prompt_len >= seq.output_len:
+                continue   # finishes by length with the token of the in-flight step
+            cont.append(seq)
+            if (len(seq.token_ids) + 1 + ps - 1) // ps > len(seq.page_table):
+                need += 1
+        if not cont or self.mm.get_num_free_pages() < need + self.num_kvthresh_pages:
+            return None
+        entries = []
+        for seq in reversed(cont):   # process_output re-queues head-first, so the next step sees the reverse order
+            idx = len(seq.token_ids)
+            seq.token_ids.append(PLACEHOLDER)
+            seq.pending = idx
+            seq.scheduled_token_num = idx + 1
+            entries.append(ScheduledSeq(seq, idx, 1))
+        self.mm.pre_allocate_page([e.seq for e in entries])
+        self.batch_running.append(entries)
+        return entries
 
     def check_abort_seqs(self) -> Optional[SchedulerOutput]:
         if not self.abort_ids:

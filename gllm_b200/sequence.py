@@ -9,7 +9,7 @@ class Sequence:
                  "finish_tokens", "output_len", "cur_length", "temperature", "top_p", "top_k",
                  "repetition_penalty", "computed_token_num", "scheduled_token_num", "is_abort",
                  "mm_contents", "page_hashes", "num_cached_tokens", "arrival_time", "first_token_time",
-                 "finish_time", "slot", "mrope_delta", "mm_state", "pt_np")
+                 "finish_time", "slot", "mrope_delta", "mm_state", "pt_np", "pending", "zombie")
 
     def __init__(self, seq_id: int, token_ids: List[int], finish_tokens: List[int],
                  output_len: Optional[int] = None, ignore_eos: bool = False, temperature: float = 0.6,
@@ -43,6 +43,8 @@ class Sequence:
         self.slot = -1  # row in the persistent per-sequence device state (penalty bitmask, ...)
         self.mrope_delta = 0
         self.pt_np = None  # numpy mirror of page_table (rebuilt only when its length changes)
+        self.pending = -1    # index of a placeholder token reserved by a lookahead step (async scheduling)
+        self.zombie = False  # finished while a lookahead step was already in flight: pages freed when it returns
         self.mm_state = None
 
     def __len__(self):
@@ -83,17 +85,23 @@ class Sequence:
         if self.mm_state:
             self.mm_state["sent"] = False  # the vision embeddings must be recomputed too
 
+    @property
+    def known_len(self) -> int:
+        """Number of tokens whose values are known on the host (a trailing lookahead placeholder is not)."""
+        return len(self.token_ids) - (1 if self.pending >= 0 else 0)
+
     def detokenize_inc(self, tokenizer) -> str:
         """Incremental detokenisation; holds back while the tail decodes to U+FFFD."""
-        if self.cur_length >= len(self.token_ids):
+        end = self.known_len
+        if self.cur_length >= end:
             return ""
         prev = tokenizer.decode(self.token_ids[self.cur_length - 1: self.cur_length + 1],
                                 skip_special_tokens=True) if self.cur_length > 0 else ""
         added_space = " " if " " in prev.strip() else ""
-        delta = tokenizer.decode(self.token_ids[self.cur_length:], skip_special_tokens=True)
+        delta = tokenizer.decode(self.token_ids[self.cur_length:end], skip_special_tokens=True)
         if delta.endswith("�"):
             return ""
         if len(delta) > 0 and delta[0] != " ":
             delta = added_space + delta
-        self.cur_length = len(self.token_ids)
+        self.cur_length = end
         return delta

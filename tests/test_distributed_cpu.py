@@ -54,3 +54,10 @@ def test_pp2_tile_streamed_recv_matches_single(single, monkeypatch):
     first layer's add+norm / QKV projection run per tile."""
     monkeypatch.setenv("GLLM_PP_TILE_ROWS", "8")
     assert _run(2, 1, port=29871) == single
+
+
+def test_tp2_async_lookahead_matches_single(single, monkeypatch):
+    """Async scheduling under TP: the lookahead batch (placeholder tokens + device-side feed indices) travels to
+    the peer rank over the packed ZeroMQ frame and every rank feeds from its own sampler output."""
+    monkeypatch.setenv("GLLM_TEST_ASYNC", "1")
+    assert _run(1, 2, port=29881) == single

@@ -230,3 +230,50 @@ def test_fp8_block_quantised_moe_experts_close_to_hf():
     same_first = sum(s.token_ids[len(p)] == _hf_greedy(m, p, 1)[0] for p, s in zip(PROMPTS, outs))
     assert same_first >= len(PROMPTS) - 1
     llm.shutdown()
+
+
+def test_async_lookahead_scheduling_is_token_exact():
+    """`async_schedule=True`: the next decode step is queued before the previous step's tokens reach the host
+    (placeholder + device-side token feed). Must reproduce HF greedy tokens, and the synchronous engine's tokens
+    with EOS finishing mid-flight (zombie sequences) and under KV pressure (preemption)."""
+    from transformers import Qwen3Config, Qwen3ForCausalLM
+    from gllm_b200 import LLM
+    from gllm_b200 import scheduler as S
+    torch.manual_seed(5)
+    cfg = Qwen3Config(hidden_size=64, intermediate_size=128, num_hidden_layers=2, num_attention_heads=4,
+                      num_key_value_heads=2, head_dim=16, vocab_size=512, max_position_embeddings=512,
+                      eos_token_id=1, tie_word_embeddings=False)
+    m = Qwen3ForCausalLM(cfg).eval().float()
+    d = _save(m)
+    looks = {"n": 0}
+    orig = S.Scheduler.schedule_lookahead
+
+    def counted(self):
+        r = orig(self)
+        looks["n"] += bool(r)
+        return r
+
+    S.Scheduler.schedule_lookahead = counted
+    try:
+        llm = _engine(d, async_schedule=True, enable_prefix_caching=False)
+        outs = llm.generate(tokens=PROMPTS, output_lens=[10] * len(PROMPTS), ignore_eos=True)
+        for p, s in zip(PROMPTS, outs):
+            assert s.token_ids[len(p):] == _hf_greedy(m, p, 10), (len(p),)
+        assert looks["n"] >= 5, "lookahead scheduling never engaged"
+        llm.shutdown()
+        # EOS finishing while a lookahead step is in flight + KV pressure: async == sync
+        gen = [t for p, s in zip(PROMPTS, outs) for t in s.token_ids[len(p):]]
+        eos = max(set(gen), key=gen.count)
+        res = {}
+        for mode in (False, True):
+            llm = _engine(d, async_schedule=mode, enable_prefix_caching=False, num_cpu_pages=40, kvthresh=0.0)
+            llm.finish_tokens = [eos]
+            o = llm.generate(tokens=PROMPTS, output_lens=[40] * len(PROMPTS), ignore_eos=False)
+            res[mode] = [s.token_ids for s in o]
+            mm = llm.worker.mm
+            assert mm.get_num_free_pages() == mm.num_pages - 1, "pages leaked"    # all but the dummy page
+            llm.shutdown()
+        assert res[False] == res[True]
+        assert any(len(x) - len(p) < 40 for x, p in zip(res[True], PROMPTS)), "EOS never hit: test is vacuous"
+    finally:
+        S.Scheduler.schedule_lookahead = orig

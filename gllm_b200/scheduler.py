@@ -113,6 +113,18 @@ class Scheduler:
 
     # -- inputs -----------------------------------------------------------------------------------
     def add_new_requests(self, seqs: List[Sequence]):
+        cap = (self.mm.num_pages - (1 if getattr(self.mm, "dummy_page", None) is not None else 0)) * self.page_size
+        for seq in seqs:
+            if len(seq) + 1 > cap:
+                # the prompt alone can never be resident: it would wait in the queue forever
+                logger.error("request %d: prompt of %d tokens but the KV cache holds %d: rejected", seq.seq_id,
+                             len(seq), cap)
+                self.abort_ids.add(seq.seq_id)
+            elif len(seq) + seq.output_len > cap:
+                # alone in the pool it would still outgrow it and be preempted/recomputed forever: cap the length
+                logger.warning("request %d: output capped to %d tokens (KV cache holds %d tokens)", seq.seq_id,
+                               cap - len(seq), cap)
+                seq.output_len = cap - len(seq)
         self.seqs_to_prefill.extend(seqs)
 
     def add_abort_ids(self, ids):

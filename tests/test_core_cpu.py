@@ -307,3 +307,21 @@ def test_incremental_decode_batch_equals_full_rebuild():
         prev = fast
         for s in seqs:
             s.token_ids.append(int(rng.integers(3, 200)))
+
+
+def test_oversized_requests_do_not_hang_the_scheduler():
+    """A prompt that can never be resident is rejected (finished with no output) and an output budget that the
+    pool cannot hold is capped — neither may block the queue forever."""
+    from gllm_b200.memory_manager import MemoryManager
+    from gllm_b200.scheduler import Scheduler
+    from gllm_b200.sequence import Sequence
+    mm = MemoryManager(8, 16, reserve_dummy_page=True)          # 7 usable pages = 112 tokens
+    sch = Scheduler(mm, maxp=32, maxd=8, page_size=16, log=False)
+    big = Sequence(1, list(range(200)), [1], 4, True)
+    greedy = Sequence(2, list(range(40)), [1], 500, True)
+    sch.add_new_requests([big, greedy])
+    assert greedy.output_len == 112 - 40
+    out = sch.check_abort_seqs()
+    assert out is not None and out.free_ids == [1] and big not in sch.seqs_to_prefill
+    ents = sch.schedule_once()
+    assert ents and ents[0].seq is greedy

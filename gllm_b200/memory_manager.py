@@ -161,7 +161,7 @@ class PrefixMemoryManager(MemoryManager):
     def pre_allocate_page(self, seqs: List[Sequence]):
         ps = self.page_size
         for seq in seqs:
-            n_tok = len(seq.token_ids)
+            n_tok = seq.known_len   # a trailing lookahead placeholder is not hashable yet (async scheduling)
             # a page completed by decode becomes cacheable
             if seq.computed_prompt and n_tok % ps == 0 and seq.page_table:
                 self._extend_hashes(seq, n_tok // ps)

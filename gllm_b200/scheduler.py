@@ -206,10 +206,10 @@ class Scheduler:
         step that follows it. The input token of every row is not known on the host yet — the sequence gets a
         PLACEHOLDER and the runner feeds the value from the previous step's device-side sampler output — so the
         GPU never waits for the host's output processing / scheduling / batch building. Returns None whenever the
-        steady-state assumptions do not hold (pending prefills, prefix caching, penalties, no KV headroom, ...),
+        steady-state assumptions do not hold (pending prefills, penalties, no KV headroom, ...),
         in which case the caller simply waits for the in-flight batch as before."""
         if self.pp_size != 1 or len(self.batch_running) != 1 or self.seqs_to_prefill or self.seqs_to_decode or \
-                self.next_tokens_queue or self.abort_ids or isinstance(self.mm, PrefixMemoryManager):
+                self.next_tokens_queue or self.abort_ids:
             return None
         base = self.batch_running[0]
         cont = []

@@ -255,12 +255,14 @@ def test_async_lookahead_scheduling_is_token_exact():
 
     S.Scheduler.schedule_lookahead = counted
     try:
-        llm = _engine(d, async_schedule=True, enable_prefix_caching=False)
-        outs = llm.generate(tokens=PROMPTS, output_lens=[10] * len(PROMPTS), ignore_eos=True)
-        for p, s in zip(PROMPTS, outs):
-            assert s.token_ids[len(p):] == _hf_greedy(m, p, 10), (len(p),)
-        assert looks["n"] >= 5, "lookahead scheduling never engaged"
-        llm.shutdown()
+        for prefix in (False, True):      # with the prefix cache, pages completed by decode are hashed one step later
+            looks["n"] = 0
+            llm = _engine(d, async_schedule=True, enable_prefix_caching=prefix)
+            outs = llm.generate(tokens=PROMPTS, output_lens=[10] * len(PROMPTS), ignore_eos=True)
+            for p, s in zip(PROMPTS, outs):
+                assert s.token_ids[len(p):] == _hf_greedy(m, p, 10), (len(p),)
+            assert looks["n"] >= 5, "lookahead scheduling never engaged"
+            llm.shutdown()
         # EOS finishing while a lookahead step is in flight + KV pressure: async == sync
         gen = [t for p, s in zip(PROMPTS, outs) for t in s.token_ids[len(p):]]
         eos = max(set(gen), key=gen.count)

@@ -170,12 +170,13 @@ class Worker(ProfilerMixin):
         self.batch_counter += 1
         batch = build_batch(entries, self.cfg.page_size, self.runner.spec.vocab_size, self.batch_counter,
                             mrope=self.runner.input_data.mrope, prev=getattr(self, "_last_batch", None))
-        if batch.feed_src is None and any(e.seq.pending == e.start for e in entries):
-            # lookahead batch that missed the incremental path: map rows to the previous step's sampler output
-            prev = self._last_batch
-            where = {sid: i for i, sid in enumerate(prev.seq_ids)}
+        if batch.feed_src is None and entries[0].seq.pending == entries[0].start:
+            # lookahead batch that did not take the incremental path (mixed base batch): the leading decode rows
+            # take their tokens from the previous step's sampler output, indexed in its emit order
             import numpy as np
-            batch.feed_src = np.asarray([where[e.seq.seq_id] for e in entries], dtype=np.int32)
+            where = {sid: i for i, sid in enumerate(self._last_batch.emit_ids)}
+            batch.feed_src = np.asarray([where[e.seq.seq_id] for e in entries if e.seq.pending == e.start],
+                                        dtype=np.int32)
         self._last_batch = batch if self.cfg.pp_size == 1 else None   # PP interleaves micro-batches
         if self.comm is not None:
             self.comm.send_batch(batch)

@@ -48,6 +48,7 @@ class BatchArrays:
     # lookahead (async scheduling): row i takes its input token from element feed_src[i] of the PREVIOUS step's
     # device-side sampler output instead of `tokens[i]` (which holds a placeholder)
     feed_src: Optional[np.ndarray] = None
+    emit_ids: Optional[list] = None  # driver-local: sequence id per EMITTING entry (order of the sampler output)
     seq_ids: Optional[list] = None  # driver-local: sequence id per row (incremental decode batches); not sent
     seq_index: Optional[dict] = None  # driver-local: seq id -> row (built lazily by the next batch)
 
@@ -146,7 +147,7 @@ def _build_decode_fast(entries, page_size: int, batch_id: int, prev: "BatchArray
         temperature=prev.temperature[perm], top_k=prev.top_k[perm], top_p=prev.top_p[perm],
         rep_penalty=prev.rep_penalty[perm], state_slot=prev.state_slot[perm], num_decode_seqs=b, num_seqs=b, num_tokens=b, max_q_len=1,
         max_seq_len=int(seq_lens.max()), all_greedy=prev.all_greedy, need_penalty=False, batch_id=batch_id,
-        seq_ids=ids)
+        seq_ids=ids, emit_ids=ids)
 
 
 def build_batch(entries, page_size: int, vocab_size: int, batch_id: int = 0, mrope: bool = False,
@@ -240,7 +241,8 @@ def build_batch(entries, page_size: int, vocab_size: int, batch_id: int = 0, mro
         seen_rows=np.concatenate(seen_rows) if seen_rows else None,
         seen_tokens=np.concatenate(seen_tokens) if seen_tokens else None,
         clear_slots=np.asarray(clear_slots, dtype=np.int32) if clear_slots else None, batch_id=batch_id, mm=mm,
-        seq_ids=[e.seq.seq_id for e in entries] if n_dec == b else None)
+        seq_ids=[e.seq.seq_id for e in entries] if n_dec == b else None,
+        emit_ids=[entries[i].seq.seq_id for i in emit_seq])
 
 
 class InputData:

@@ -206,10 +206,10 @@ class Scheduler:
         step that follows it. The input token of every row is not known on the host yet — the sequence gets a
         PLACEHOLDER and the runner feeds the value from the previous step's device-side sampler output — so the
         GPU never waits for the host's output processing / scheduling / batch building. Returns None whenever the
-        steady-state assumptions do not hold (pending prefills, penalties, no KV headroom, ...),
+        assumptions do not hold (more runnable sequences than one batch, penalties, split_pd, no KV headroom, ...),
         in which case the caller simply waits for the in-flight batch as before."""
-        if self.pp_size != 1 or len(self.batch_running) != 1 or self.seqs_to_prefill or self.seqs_to_decode or \
-                self.next_tokens_queue or self.abort_ids:
+        if self.pp_size != 1 or len(self.batch_running) != 1 or self.seqs_to_decode or self.next_tokens_queue or \
+                self.abort_ids or self.schedule_method == "split_pd":
             return None
         base = self.batch_running[0]
         cont = []
@@ -217,7 +217,9 @@ class Scheduler:
         need = 0
         for ent in base:
             seq = ent.seq
-            if not ent.is_decode or seq.pending >= 0 or seq.repetition_penalty != 1.0 or seq.mm_state:
+            if not ent.emits:
+                continue   # unfinished prefill chunk: its continuation is ordinary prefill work (tokens known)
+            if seq.pending >= 0 or seq.repetition_penalty != 1.0 or seq.mm_state:
                 return None
             if seq.is_abort or seq.zombie:
                 continue
@@ -226,7 +228,9 @@ class Scheduler:
             cont.append(seq)
             if (len(seq.token_ids) + 1 + ps - 1) // ps > len(seq.page_table):
                 need += 1
-        if not cont or self.mm.get_num_free_pages() < need + self.num_kvthresh_pages:
+        if len(cont) > min(self.maxd, self.maxp) or self.mm.get_num_free_pages() < need + self.num_kvthresh_pages:
+            return None
+        if not cont and not self.seqs_to_prefill:
             return None
         entries = []
         for seq in reversed(cont):   # process_output re-queues head-first, so the next step sees the reverse order
@@ -236,6 +240,23 @@ class Scheduler:
             seq.scheduled_token_num = idx + 1
             entries.append(ScheduledSeq(seq, idx, 1))
         self.mm.pre_allocate_page([e.seq for e in entries])
+        n_prefill = 0
+        if self.seqs_to_prefill:
+            # new / continuing prompts ride along exactly as in the synchronous policies (their tokens are known)
+            headroom = kv_headroom_tokens(self.mm.get_num_free_pages(), self.num_kvthresh_pages, self.page_size)
+            if self.schedule_method == "token_throttling":
+                if self.world_size > 1 and headroom != 0:
+                    self.update_num_wait_tokens()
+                budget = throttled_prefill_budget(headroom, self.world_size, self.mm.get_memory_free(), self.kvthresh,
+                                                  self.maxp, self.minp, self.iterp, len(self.seqs_to_prefill),
+                                                  self.num_wait_tokens)
+            else:
+                budget = min(self.maxp - len(entries), headroom)
+            prefill_batch, n_prefill = self.schedule_prefill_batch(budget)
+            entries = entries + prefill_batch
+        if not entries:
+            return None
+        self._log_status(len(cont), n_prefill, len(cont))
         self.batch_running.append(entries)
         return entries
 

@@ -277,5 +277,22 @@ def test_async_lookahead_scheduling_is_token_exact():
             llm.shutdown()
         assert res[False] == res[True]
         assert any(len(x) - len(p) < 40 for x, p in zip(res[True], PROMPTS)), "EOS never hit: test is vacuous"
+        # requests arriving while others decode (mixed lookahead batches: decode rows fed from the device + new
+        # prefill chunks with known tokens)
+        staged = {}
+        for mode in (False, True):
+            llm = _engine(d, async_schedule=mode, maxp=32)
+            seqs = [llm.allocate_seq(p, n, True, top_k=1) for p, n in zip(PROMPTS, (30, 12, 20, 25))]
+            llm.add_requests(seqs[:1])
+            n = 0
+            while len(llm.finished) < len(seqs):
+                llm.schedule()
+                n += 1
+                if n in (6, 11, 15):
+                    llm.add_requests([seqs[(6, 11, 15).index(n) + 1]])
+                assert n < 5000
+            staged[mode] = [s.token_ids for s in seqs]
+            llm.shutdown()
+        assert staged[False] == staged[True]
     finally:
         S.Scheduler.schedule_lookahead = orig

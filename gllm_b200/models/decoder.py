@@ -393,7 +393,8 @@ class CausalLM(nn.Module):
                 flat = p.data.view(-1)
                 for s0 in range(0, flat.numel(), step):
                     e0 = min(s0 + step, flat.numel())
-                    flat[s0:e0].copy_((torch.randn(e0 - s0, device=p.device) * 100.0).to(torch.float8_e4m3fn))
+                    flat[s0:e0].copy_((torch.randn(e0 - s0, device=p.device) * 100.0).clamp_(-448.0, 448.0)
+                                     .to(torch.float8_e4m3fn))   # e4m3fn has no inf: out-of-range casts give NaN
             elif name.endswith("_ws"):
                 p.data.fill_(0.02 / 100.0)
             elif p.is_cuda:

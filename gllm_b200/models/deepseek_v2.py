@@ -261,6 +261,11 @@ def spec_deepseek(cfg) -> ModelSpec:
     spec.extra = {k: cfg.get(k) for k in ("q_lora_rank", "kv_lora_rank", "qk_nope_head_dim", "qk_rope_head_dim",
                                           "v_head_dim")}
     spec.names = {"shared": "mlp.shared_experts.", "router_bias": "mlp.gate.e_score_correction_bias"}
+    qc = cfg.get("quantization_config") or {}
+    if qc.get("quant_method") == "fp8" and list(qc.get("weight_block_size") or []) == [128, 128]:
+        # the routed experts (97 % of the parameters) stay block-scaled e4m3 — that is what lets V3 / R1 fit on
+        # 8 x 180 GB; the MLA projections and the dense / shared MLPs are de-quantised to bf16 at load
+        spec.quant = "fp8"
     return spec
 
 

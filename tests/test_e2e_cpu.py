@@ -296,3 +296,30 @@ def test_async_lookahead_scheduling_is_token_exact():
         assert staged[False] == staged[True]
     finally:
         S.Scheduler.schedule_lookahead = orig
+
+
+def test_deepseek_fp8_checkpoint_keeps_experts_quantised():
+    """DeepSeek-V3-style fp8 checkpoints: the routed experts stay block-scaled e4m3 (what lets V3 fit on 8 GPUs),
+    MLA / dense / shared weights are de-quantised; first tokens agree with the unquantised HF model."""
+    import json
+    from transformers import DeepseekV3Config, DeepseekV3ForCausalLM
+    torch.manual_seed(13)
+    cfg = DeepseekV3Config(hidden_size=256, intermediate_size=256, moe_intermediate_size=128, num_hidden_layers=2,
+                           num_attention_heads=4, num_key_value_heads=4, n_routed_experts=4, n_shared_experts=1,
+                           num_experts_per_tok=2, n_group=2, topk_group=1, first_k_dense_replace=1,
+                           routed_scaling_factor=1.0, norm_topk_prob=True, q_lora_rank=32, kv_lora_rank=32,
+                           qk_nope_head_dim=16, qk_rope_head_dim=8, v_head_dim=16, vocab_size=512,
+                           max_position_embeddings=512, eos_token_id=1, rope_scaling=None, rope_interleave=True)
+    m = DeepseekV3ForCausalLM(cfg).eval().float()
+    d = _save(m)
+    c = json.load(open(os.path.join(d, "config.json")))
+    c["quantization_config"] = {"quant_method": "fp8", "activation_scheme": "dynamic", "fmt": "e4m3",
+                                "weight_block_size": [128, 128]}
+    json.dump(c, open(os.path.join(d, "config.json"), "w"))
+    llm = _engine(d)
+    ex = llm.worker.runner.model.layers[1].mlp.experts
+    assert ex.quant == "fp8" and ex.w13.dtype == torch.float8_e4m3fn
+    outs = llm.generate(tokens=PROMPTS, output_lens=[4] * len(PROMPTS), ignore_eos=True)
+    same_first = sum(s.token_ids[len(p)] == _hf_greedy(m, p, 1)[0] for p, s in zip(PROMPTS, outs))
+    assert same_first >= len(PROMPTS) - 1
+    llm.shutdown()

@@ -125,3 +125,20 @@ def test_mrope_positions_text_image_text():
     assert pos[2, 3:9].tolist() == [3, 4, 5, 3, 4, 5]
     assert pos[:, 9:].tolist() == [[6, 7]] * 3       # continues at max + 1
     assert delta == 8 - len(ids)
+
+
+def test_mrope_positions_video_temporal_spacing():
+    """Qwen2.5-VL video: one placeholder run of t*h*w tokens, temporal index = frame * second_per_grid *
+    tokens_per_second (reference: gllm/layers/rotary_embedding.py:697-707); Qwen3-VL: one run per frame."""
+    from gllm_b200.models.multimodal import MMInfo, compute_mrope_positions
+    info = MMInfo(image_token_id=IMG, video_token_id=VID, spatial_merge_size=2, tokens_per_second=2.0)
+    ids = [1, VSTART] + [VID] * 12 + [3]          # grid 3 x 4 x 4 -> 3 frames of 2 x 2 merged tokens
+    pos, delta = compute_mrope_positions(ids, None, [(3, 4, 4)], info, second_per_grid_ts=[1.0])
+    assert pos[0, 2:14].tolist() == [2] * 4 + [4] * 4 + [6] * 4           # start 2, frames 0/2/4 apart
+    assert pos[1, 2:14].tolist() == [2, 2, 3, 3] * 3 and pos[2, 2:14].tolist() == [2, 3, 2, 3] * 3
+    assert pos[:, 14].tolist() == [7, 7, 7] and delta == 8 - len(ids)
+    info3 = MMInfo(image_token_id=IMG, video_token_id=VID, spatial_merge_size=2, per_frame_video=True)
+    ids3 = [1] + [VID] * 4 + [9] + [VID] * 4 + [3]   # two frames of one video, a timestamp token in between
+    pos3, _ = compute_mrope_positions(ids3, None, [(2, 4, 4)], info3)
+    assert pos3[0, 1:5].tolist() == [1] * 4 and pos3[1, 1:5].tolist() == [1, 1, 2, 2]
+    assert pos3[:, 5].tolist() == [3, 3, 3] and pos3[0, 6:10].tolist() == [4] * 4

@@ -84,8 +84,15 @@ def load():
         raise _LIB_ERR
     try:
         if not os.path.exists(LIB_PATH):
-            raise FileNotFoundError(
-                f"{LIB_PATH} not found — run `python -m gllm_b200.build` (or __graft_entry__.build())")
+            # safety net: build in-tree on first use when a toolchain is present (takes about a minute); a box
+            # without nvcc gets the loud error — there is no PyTorch fallback on the GPU path
+            try:
+                from gllm_b200 import build as _build
+                _build.build()
+            except Exception as be:  # noqa: BLE001
+                raise FileNotFoundError(
+                    f"{LIB_PATH} not found and the in-tree build failed ({be}) — run `python -m gllm_b200.build` "
+                    f"(or __graft_entry__.build())") from be
         lib = ctypes.CDLL(LIB_PATH)
         _declare(lib)
         _LIB = lib

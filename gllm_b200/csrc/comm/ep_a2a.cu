@@ -87,8 +87,8 @@ __global__ void ep_dispatch_kernel(const __nv_bfloat16* __restrict__ x, int64_t 
 __global__ void ep_wait_kernel(const uint32_t* flags, const EpState* st, int ep) {
   if (threadIdx.x < ep) {
     const uint32_t call = *reinterpret_cast<const volatile uint32_t*>(&st->calls);
-    while (static_cast<int32_t>(ld_acquire_sys(flags + threadIdx.x) - call) < 0) {
-    }
+    SpinGuard guard;
+    while (static_cast<int32_t>(ld_acquire_sys(flags + threadIdx.x) - call) < 0) guard.poll();
   }
 }
 
@@ -119,8 +119,8 @@ __global__ void ep_combine_kernel(const __nv_bfloat16* __restrict__ comb, const 
                                   int n_rows, int top_k, int H) {
   if (threadIdx.x < ep) {
     const uint32_t call = *reinterpret_cast<const volatile uint32_t*>(&st->calls);
-    while (static_cast<int32_t>(ld_acquire_sys(ctrl + kCtrlReturn + threadIdx.x) - call) < 0) {
-    }
+    SpinGuard guard;
+    while (static_cast<int32_t>(ld_acquire_sys(ctrl + kCtrlReturn + threadIdx.x) - call) < 0) guard.poll();
   }
   __syncthreads();
   if (blockIdx.x == 0 && threadIdx.x == 0) ctrl[kCtrlPool] = 0;

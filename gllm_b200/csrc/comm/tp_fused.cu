@@ -93,8 +93,8 @@ __global__ void rs_reduce_norm_kernel(const ReduceNormParams p) {
     const uint32_t target = p.st->rs_expected[p.parity][src] + p.n_tiles[src];
     const uint32_t* c = p.cnt + src;
     // wrap-safe comparison on monotonically increasing counters
-    while (static_cast<int32_t>(ld_acquire_sys(c) - target) < 0) {
-    }
+    SpinGuard guard;
+    while (static_cast<int32_t>(ld_acquire_sys(c) - target) < 0) guard.poll();
   }
   __syncthreads();
 
@@ -266,6 +266,7 @@ __global__ void ll_allreduce_norm_kernel(const LLParams p) {
   }
   float a[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   if (active) {
+    SpinGuard guard;
     const uint2* mybuf = p.ll_peers[p.rank];
     for (int s = 0; s < p.tp; ++s) {
       uint32_t w[4];
@@ -277,7 +278,11 @@ __global__ void ll_allreduce_norm_kernel(const LLParams p) {
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
           uint2 v;
-          do { v = ld_volatile_v2(src + k); } while (v.y != epoch);
+          v = ld_volatile_v2(src + k);
+          while (v.y != epoch) {
+            guard.poll();
+            v = ld_volatile_v2(src + k);
+          }
           w[k] = v.x;
         }
       }
@@ -366,8 +371,8 @@ __global__ void push_partial_rows_kernel(const __nv_bfloat16* __restrict__ x, in
 __global__ void wait_ag_flags_kernel(const uint32_t* flags, const TpState* st, int ag_idx, int nblk) {
   for (int b = threadIdx.x; b < nblk; b += blockDim.x) {
     const uint32_t e = st->ag_expected[ag_idx][b];
-    while (static_cast<int32_t>(ld_acquire_sys(flags + b) - e) < 0) {
-    }
+    SpinGuard guard;
+    while (static_cast<int32_t>(ld_acquire_sys(flags + b) - e) < 0) guard.poll();
   }
 }
 

@@ -345,6 +345,23 @@ __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
 __device__ __forceinline__ void red_add_release_sys(uint32_t* p, uint32_t v) {
   asm volatile("red.release.sys.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
+// Bounded spin for cross-GPU / cross-CTA flag waits: a peer that died (or a lost signal) must not hang this GPU
+// forever — after kSpinTimeoutNs the kernel traps and the host sees a CUDA error (fail-stop, like the worker
+// liveness check on the host side). The clock is read once per 1024 polls, so the wait loops stay tight.
+static constexpr unsigned long long kSpinTimeoutNs = 30ull * 1000ull * 1000ull * 1000ull;
+struct SpinGuard {
+  unsigned long long t0 = 0;
+  unsigned n = 0;
+  __device__ __forceinline__ void poll() {
+    if ((++n & 0x3ffu) == 0u) {
+      unsigned long long t;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+      if (t0 == 0) t0 = t;
+      else if (t - t0 > kSpinTimeoutNs) __trap();
+    }
+  }
+};
+
 // programmatic dependent launch (host side: host_utils.h launch_pdl). Both are no-ops for a normal launch.
 __device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void griddep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }

@@ -167,8 +167,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           // all-gather ⊕ GEMM: the 128-row block `mt` of A is complete once its arrival counter reached
           // the device-resident expected value (advanced by rs_reduce_norm, comm/tp_fused.cu)
           const uint32_t want = *reinterpret_cast<const volatile uint32_t*>(p.a_expected + mt);
-          while (static_cast<int32_t>(ld_acquire_sys(p.a_ready + mt) - want) < 0) {
-          }
+          SpinGuard guard;
+          while (static_cast<int32_t>(ld_acquire_sys(p.a_ready + mt) - want) < 0) guard.poll();
           asm volatile("fence.proxy.async;" ::: "memory");
         }
         for (int kb = kb0; kb < kb1; ++kb, ++it) {
@@ -285,8 +285,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         asm volatile("bar.sync 1, 128;" ::: "memory");
         if (warp == 2 && lane == 0) {
           atomicAdd(p.tile_cnt + 2 * tile, 1u);
-          while (ld_acquire_gpu(p.tile_cnt + 2 * tile) < static_cast<uint32_t>(split)) {
-          }
+          SpinGuard guard;
+          while (ld_acquire_gpu(p.tile_cnt + 2 * tile) < static_cast<uint32_t>(split)) guard.poll();
         }
         asm volatile("bar.sync 1, 128;" ::: "memory");
       }

@@ -256,7 +256,18 @@ class Worker(ProfilerMixin):
         elif name == "stop":
             self.stop = True
 
+    def _maybe_inject_fault(self):
+        """`GLLM_FAULT_INJECT=<rank>:<step>` kills this worker once it has run <step> engine steps — exercises the
+        fail-stop contract (worker marks itself dead, the front-end exits non-zero) in tests."""
+        spec = os.environ.get("GLLM_FAULT_INJECT")
+        if not spec or self.runner is None:
+            return
+        r, n = spec.split(":")
+        if int(r) == self.rank and self.runner.stats["steps"] >= int(n):
+            raise RuntimeError(f"fault injected on rank {self.rank} after {n} steps (GLLM_FAULT_INJECT)")
+
     def step(self) -> bool:
+        self._maybe_inject_fault()
         self._reap_sends()
         if self.rank == 0:
             return self.run_driver()

@@ -29,6 +29,9 @@ from gllm_b200.parallel import state as ps
 from gllm_b200.parallel.tp import TPComm
 
 
+_NVTX = __import__("os").environ.get("GLLM_NVTX", "0") == "1"   # per-layer NVTX ranges for nsys / ncu --nvtx
+
+
 @dataclass
 class MoESpec:
     num_experts: int
@@ -340,7 +343,12 @@ class CausalLM(nn.Module):
                         for w in works:
                             w.wait()
                 h, residual = Fn.rmsnorm(hidden, self.layers[0].input_norm_w, eps, residual)
+        nvtx = _NVTX and h.is_cuda
         for i, layer in enumerate(self.layers):
+            if nvtx:
+                if i:
+                    torch.cuda.nvtx.range_pop()
+                torch.cuda.nvtx.range_push(f"layer{layer.layer_id}")
             if i + 1 < n:
                 nxt = self.layers[i + 1].input_norm_w
             else:
@@ -355,6 +363,8 @@ class CausalLM(nn.Module):
                 h, residual = layer(inp, h, residual, kv_cache, tpc, nxt, qkv=qkv0)
             else:
                 h, residual = layer(inp, h, residual, kv_cache, tpc, nxt)
+        if nvtx and n:
+            torch.cuda.nvtx.range_pop()
         return h, residual
 
     def compute_logits(self, inp, hidden: torch.Tensor, tpc: TPComm, all_rows: bool = False,

@@ -136,3 +136,27 @@ if __name__ == "__main__":
             ps.wait(timeout=10)
         except Exception:  # noqa: BLE001
             ps.kill()
+
+
+def test_fault_injection_front_end_exits_non_zero():
+    """Fail-stop contract: a worker that dies marks itself dead and the front-end process exits non-zero
+    (reference: llm_engine.py:108-117, worker.py:239-249). `GLLM_FAULT_INJECT=<rank>:<step>` kills rank 1 of a
+    PP=2 engine after a few steps."""
+    code = f"""
+import sys
+sys.path.insert(0, {ROOT!r})
+if __name__ == "__main__":
+    from gllm_b200 import LLM
+    from gllm_b200.models.presets import tiny
+    llm = LLM(tiny("Qwen3ForCausalLM", num_hidden_layers=4), load_format="dummy", pp_size=2, tp_size=1, maxp=48,
+              maxd=16, num_cpu_pages=128, model_max_length=256, log_stats=False, device="cpu",
+              master_port={_free_port()})
+    llm.generate(tokens=[[5, 17, 99], [9] * 40], output_lens=[60, 60], ignore_eos=True)
+    print("SHOULD_NOT_REACH")
+"""
+    f = tempfile.mktemp(suffix=".py")
+    open(f, "w").write(code)
+    env = dict(os.environ, GLLM_B200_LOG="WARNING", GLLM_FAULT_INJECT="1:5")
+    r = subprocess.run([sys.executable, f], env=env, capture_output=True, text=True, timeout=240)
+    assert r.returncode != 0 and "SHOULD_NOT_REACH" not in r.stdout, r.stdout[-1000:] + r.stderr[-2000:]
+    assert "fault injected" in (r.stdout + r.stderr)

@@ -325,3 +325,49 @@ def test_oversized_requests_do_not_hang_the_scheduler():
     assert out is not None and out.free_ids == [1] and big not in sch.seqs_to_prefill
     ents = sch.schedule_once()
     assert ents and ents[0].seq is greedy
+
+
+@pytest.mark.parametrize("tp", [1, 2, 4, 8])
+def test_weight_sharding_round_trip(tp):
+    """Random HF-layout tensors -> per-rank shards (reference: gllm/models/weight_utils.py:6-84) -> reassembled ==
+    original, for QKV (incl. KV-head replication when tp > kv heads), gate/up, row / column splits, the padded
+    vocabulary, contiguous expert blocks and the PP layer partition."""
+    import torch
+    from gllm_b200.models import weight_utils as wu
+    from gllm_b200.parallel.state import partition_layers
+    torch.manual_seed(tp)
+    heads, kv_heads, d, h, inter, vocab = 8, 2, 4, 16, 24 * 8, 1000
+    q, k, v = torch.randn(heads * d, h), torch.randn(kv_heads * d, h), torch.randn(kv_heads * d, h)
+    hq = heads // tp
+    qs, ks, vs = [], {}, {}
+    for r in range(tp):
+        w = wu.shard_qkv(q, k, v, heads, kv_heads, d, r, tp)
+        kv0, nkv = wu.kv_head_range(kv_heads, r, tp)
+        assert w.shape[0] == (hq + 2 * nkv) * d
+        qs.append(w[: hq * d])
+        for j in range(nkv):
+            ks[kv0 + j] = w[hq * d + j * d: hq * d + (j + 1) * d]
+            vs[kv0 + j] = w[(hq + nkv) * d + j * d: (hq + nkv) * d + (j + 1) * d]
+    assert torch.equal(torch.cat(qs), q)
+    assert torch.equal(torch.cat([ks[i] for i in range(kv_heads)]), k)
+    assert torch.equal(torch.cat([vs[i] for i in range(kv_heads)]), v)
+    gate, up, down = torch.randn(inter, h), torch.randn(inter, h), torch.randn(h, inter)
+    gu = [wu.shard_gate_up(gate, up, r, tp) for r in range(tp)]
+    assert torch.equal(torch.cat([g[: inter // tp] for g in gu]), gate)
+    assert torch.equal(torch.cat([g[inter // tp:] for g in gu]), up)
+    assert torch.equal(torch.cat([wu.shard_cols(down, r, tp) for r in range(tp)], dim=1), down)
+    emb = torch.randn(vocab, h)
+    sh = [wu.shard_vocab(emb, r, tp) for r in range(tp)]
+    full = torch.cat(sh)
+    assert full.shape[0] == wu.pad_vocab(vocab, tp) and torch.equal(full[:vocab], emb) and not full[vocab:].any()
+    for e_total in (8, 60, 257):
+        covered = []
+        for r in range(tp):
+            s0, n = wu.expert_range(e_total, r, tp)
+            covered += list(range(s0, s0 + n))
+        assert covered == list(range(e_total))
+    for layers in (36, 61, 7):
+        for pp in (1, 2, 4):
+            parts = partition_layers(layers, pp)
+            assert [i for p in parts for i in p] == list(range(layers)) and all(len(p) > 0 for p in parts)
+    assert [len(p) for p in partition_layers(64, 4, [16, 16, 17, 15])] == [16, 16, 17, 15]

@@ -14,6 +14,40 @@ from gllm_b200.engine.llm_engine import LLM
 from gllm_b200.utils.logging import logger
 
 
+class Histogram:
+    """Cumulative-bucket latency histogram in the Prometheus exposition layout (seconds)."""
+
+    def __init__(self, bounds):
+        self.bounds = tuple(bounds)
+        self.counts = [0] * (len(self.bounds) + 1)
+        self.sum = 0.0
+        self.count = 0
+
+    def observe(self, v: float):
+        self.sum += v
+        self.count += 1
+        for i, b in enumerate(self.bounds):
+            if v <= b:
+                self.counts[i] += 1
+                return
+        self.counts[-1] += 1
+
+    def lines(self, name: str) -> List[str]:
+        out, acc = [f"# TYPE {name} histogram"], 0
+        for b, c in zip(self.bounds, self.counts):
+            acc += c
+            out.append(f'{name}_bucket{{le="{b:g}"}} {acc}')
+        out.append(f'{name}_bucket{{le="+Inf"}} {self.count}')
+        out.append(f"{name}_sum {self.sum:.6f}")
+        out.append(f"{name}_count {self.count}")
+        return out
+
+
+TTFT_BUCKETS = (0.005, 0.01, 0.02, 0.04, 0.06, 0.08, 0.1, 0.25, 0.5, 0.75, 1.0, 2.5, 5.0, 7.5, 10.0, 30.0)
+TPOT_BUCKETS = (0.002, 0.004, 0.006, 0.008, 0.01, 0.015, 0.02, 0.03, 0.04, 0.05, 0.075, 0.1, 0.2, 0.5, 1.0)
+E2E_BUCKETS = (0.1, 0.25, 0.5, 1.0, 2.5, 5.0, 10.0, 20.0, 40.0, 60.0, 120.0, 300.0)
+
+
 class AsyncStream:
     def __init__(self, raw_request=None):
         self._queue: asyncio.Queue = asyncio.Queue()
@@ -66,6 +100,8 @@ class AsyncLLM(LLM):
         self._pending_tokens: List = []
         self.metrics = {"requests_total": 0, "requests_finished": 0, "requests_aborted": 0,
                         "prompt_tokens_total": 0, "generation_tokens_total": 0, "ttft_sum": 0.0, "ttft_count": 0}
+        self.hist = {"ttft": Histogram(TTFT_BUCKETS), "tpot": Histogram(TPOT_BUCKETS),
+                     "e2e": Histogram(E2E_BUCKETS)}
 
     async def add_requests_async(self, raw_request, token_ids: List[int], output_len=None, ignore_eos=False,
                                  temperature=None, top_p=None, top_k=None, repetition_penalty=None,
@@ -125,6 +161,7 @@ class AsyncLLM(LLM):
                 st.first_token_time = time.time()
                 self.metrics["ttft_sum"] += st.first_token_time - st.created
                 self.metrics["ttft_count"] += 1
+                self.hist["ttft"].observe(st.first_token_time - st.created)
             st.completion_tokens = seq.num_output_tokens
             if self.tokenizer is not None:
                 delta = seq.detokenize_inc(self.tokenizer)
@@ -140,6 +177,10 @@ class AsyncLLM(LLM):
                 st.completion_tokens = seq.num_output_tokens
                 self.metrics["generation_tokens_total"] += seq.num_output_tokens
                 self.metrics["requests_finished"] += 1
+                now = time.time()
+                self.hist["e2e"].observe(now - st.created)
+                if st.first_token_time is not None and seq.num_output_tokens > 1:
+                    self.hist["tpot"].observe((now - st.first_token_time) / (seq.num_output_tokens - 1))
                 reason = "length" if seq.num_output_tokens >= seq.output_len else "stop"
                 st.finish("abort" if seq.is_abort else reason)
         self.finished = []

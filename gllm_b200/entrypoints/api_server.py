@@ -142,9 +142,9 @@ def build_app(engine):
             "# TYPE gllm_requests_aborted_total counter", f"gllm_requests_aborted_total {m['requests_aborted']}",
             "# TYPE gllm_prompt_tokens_total counter", f"gllm_prompt_tokens_total {m['prompt_tokens_total']}",
             "# TYPE gllm_generation_tokens_total counter", f"gllm_generation_tokens_total {m['generation_tokens_total']}",
-            "# TYPE gllm_time_to_first_token_seconds summary",
-            f"gllm_time_to_first_token_seconds_sum {m['ttft_sum']:.6f}",
-            f"gllm_time_to_first_token_seconds_count {m['ttft_count']}",
+            *llm.hist["ttft"].lines("gllm_time_to_first_token_seconds"),
+            *llm.hist["tpot"].lines("gllm_time_per_output_token_seconds"),
+            *llm.hist["e2e"].lines("gllm_e2e_request_latency_seconds"),
             "# TYPE gllm_num_requests_running gauge", f"gllm_num_requests_running {len(llm.running_maps)}",
             "# TYPE gllm_num_requests_waiting gauge", f"gllm_num_requests_waiting {s.get('wait', 0)}",
             "# TYPE gllm_kv_cache_usage_perc gauge", f"gllm_kv_cache_usage_perc {s.get('memory_util', 0.0)}",

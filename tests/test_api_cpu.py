@@ -117,3 +117,8 @@ def test_engine_metrics_after_requests(client):
     assert engine.metrics["requests_finished"] >= 4
     assert engine.metrics["generation_tokens_total"] > 0
     assert len(engine.running_maps) == 0
+    text = c.get("/metrics").text
+    for name in ("time_to_first_token", "time_per_output_token", "e2e_request_latency"):
+        assert f'gllm_{name}_seconds_bucket{{le="+Inf"}}' in text
+    h = engine.hist["ttft"]
+    assert h.count == sum(h.counts) >= 4 and engine.hist["tpot"].count > 0

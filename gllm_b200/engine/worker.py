@@ -49,6 +49,7 @@ class Worker(ProfilerMixin):
         self.mp_alive, self.mp_progress = mp_alive, mp_progress
         self.runner: Optional[ModelRunner] = None
         self.scheduler: Optional[Scheduler] = None
+        self.phase_stats = {f"{p}_step_{k}": 0 for p in ("prefill", "decode") for k in ("seconds", "count", "tokens")}
         self.pending: Deque = deque()          # driver: (batch_id, StepResult) whose tokens are not read yet
         self.peer_batches: Deque[BatchArrays] = deque()
         self.inflight_sends: Deque = deque()   # keep isend handles alive (reference drops them)
@@ -117,6 +118,7 @@ class Worker(ProfilerMixin):
                          free_ids=out.free_ids)
         if self.scheduler is not None:
             pkg.stats = dict(self.scheduler.last_stats)
+            pkg.stats.update(self.phase_stats)
         if self.comm is not None and self.comm.sock_fe_out is not None and not self.comm.frontend:
             self.comm.send_frontend(pkg)
         else:
@@ -146,10 +148,14 @@ class Worker(ProfilerMixin):
         keep = 1 if (self.cfg.async_schedule and len(self.pending) == 2) else 0   # the step queued just now
         # tokens of our own finished micro-batches
         while len(self.pending) > keep:
-            bid, res = self.pending[0]
+            bid, res, t0, phase, ntok = self.pending[0]
             if res.event is not None and not res.event.query():
                 break
             self.pending.popleft()
+            # per-phase step accounting for /metrics: launch -> tokens-ready wall time of this micro-batch
+            self.phase_stats[phase + "_step_seconds"] += time.perf_counter() - t0
+            self.phase_stats[phase + "_step_count"] += 1
+            self.phase_stats[phase + "_step_tokens"] += ntok
             sch.add_next_tokens(res.tokens_list())
             did = True
         while True:
@@ -168,6 +174,7 @@ class Worker(ProfilerMixin):
 
     def _launch(self, entries):
         self.batch_counter += 1
+        t0 = time.perf_counter()
         batch = build_batch(entries, self.cfg.page_size, self.runner.spec.vocab_size, self.batch_counter,
                             mrope=self.runner.input_data.mrope, prev=getattr(self, "_last_batch", None))
         if batch.feed_src is None and entries[0].seq.pending == entries[0].start:
@@ -183,7 +190,8 @@ class Worker(ProfilerMixin):
         res = self.runner.step(batch)
         if ps.is_last_pp_rank():
             if ps.is_output_rank():
-                self.pending.append((batch.batch_id, res))
+                phase = "decode" if batch.num_decode_seqs == batch.num_seqs else "prefill"
+                self.pending.append((batch.batch_id, res, t0, phase, batch.num_tokens))
         else:
             self._pp_send(res)
 

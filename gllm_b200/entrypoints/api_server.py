@@ -151,6 +151,12 @@ def build_app(engine):
             "# TYPE gllm_prefix_cache_hit_rate gauge", f"gllm_prefix_cache_hit_rate {s.get('cache_hit_rate', 0.0)}",
             "# TYPE gllm_num_preemptions_total counter", f"gllm_num_preemptions_total {s.get('preempted', 0)}",
         ]
+        # per-phase step accounting from the driver worker (launch -> tokens-ready time of every micro-batch;
+        # a batch that carries any prefill chunk counts as prefill)
+        for key, kind in (("seconds", "seconds"), ("count", "iterations"), ("tokens", "tokens")):
+            lines.append(f"# TYPE gllm_step_{kind}_total counter")
+            for ph in ("prefill", "decode"):
+                lines.append(f'gllm_step_{kind}_total{{phase="{ph}"}} {s.get(f"{ph}_step_{key}", 0):.6g}')
         return PlainTextResponse("\n".join(lines) + "\n")
 
     @app.get("/v1/models")

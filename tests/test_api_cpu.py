@@ -120,5 +120,7 @@ def test_engine_metrics_after_requests(client):
     text = c.get("/metrics").text
     for name in ("time_to_first_token", "time_per_output_token", "e2e_request_latency"):
         assert f'gllm_{name}_seconds_bucket{{le="+Inf"}}' in text
+    assert 'gllm_step_seconds_total{phase="decode"}' in text and engine.last_stats["decode_step_count"] > 0
+    assert engine.last_stats["prefill_step_tokens"] > 0 and engine.last_stats["decode_step_seconds"] > 0
     h = engine.hist["ttft"]
     assert h.count == sum(h.counts) >= 4 and engine.hist["tpot"].count > 0

@@ -114,5 +114,9 @@ def build(force: bool = False, verbose: bool = False) -> str:
     return LIB_PATH
 
 
-if __name__ == "__main__":
+def main():
     build(force="--force" in sys.argv, verbose="--verbose" in sys.argv)
+
+
+if __name__ == "__main__":
+    main()

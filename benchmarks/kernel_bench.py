@@ -102,10 +102,18 @@ def bench_attn():
         q = torch.randn(b * ql, hq * d, device="cuda").bfloat16()
         out = torch.empty_like(q)
         scale = 1 / math.sqrt(d)
-        ms = timeit(lambda: sm100.paged_attention(q, kc, vc, bt, sl, qsl, scale, hq, d, 0, b, ql, ql, out=out), iters=10)
         flops = 4.0 * b * hq * d * ql * ql / 2
-        print(json.dumps({"kernel": "attn_prefill", "B": b, "q_len": ql, "ms": round(ms, 4),
-                          "tflops": round(flops / ms / 1e9, 1)}), flush=True)
+        variants = [("mma.sync", False, 0)]
+        if os.environ.get("KB_ATTN_TC", "0") == "1":      # opt-in tcgen05 kernel, both KV tile sizes
+            variants += [("tcgen05", True, 128), ("tcgen05", True, 64)]
+        for name, tc, kvt in variants:
+            sm100.ATTN_TC, sm100.ATTN_TC_KV = tc, (kvt or 128)
+            ms = timeit(lambda: sm100.paged_attention(q, kc, vc, bt, sl, qsl, scale, hq, d, 0, b, ql, ql, out=out),
+                        iters=10)
+            print(json.dumps({"kernel": "attn_prefill", "impl": name, "kv_tile": kvt, "B": b, "q_len": ql,
+                              "ms": round(ms, 4), "tflops": round(flops / ms / 1e9, 1),
+                              "frac_of_measured_bf16": round(flops / ms / 1e9 / PEAKS["bf16_tflops"], 3)}), flush=True)
+        sm100.ATTN_TC = False
 
 
 def bench_mla():

@@ -225,6 +225,10 @@ def rope_kv_write(q: torch.Tensor, k: torch.Tensor, v: Optional[torch.Tensor], p
 # ----------------------------------------------------------------------------------------------
 _attn_ws = {}
 _FUSED_MERGE = os.environ.get("GLLM_ATTN_FUSED_MERGE", "0") == "1"
+# tcgen05 / TMEM prefill attention (csrc/attn/prefill_attention_tc.cu): opt-in until validated on hardware.
+# ATTN_TC_KV = keys per pipeline stage (64 or 128). Module attributes so tests / benches can flip them.
+ATTN_TC = os.environ.get("GLLM_ATTN_TC", "0") == "1"
+ATTN_TC_KV = int(os.environ.get("GLLM_ATTN_TC_KV", "128"))
 
 
 def decode_splits(num_seqs: int, num_kv_heads: int, num_q_heads: int, max_seq_len: int) -> int:
@@ -298,6 +302,15 @@ def paged_attention(q: torch.Tensor, k_cache: torch.Tensor, v_cache: torch.Tenso
     n_prefill = num_seqs - num_decode_seqs
     if n_prefill > 0:
         assert query_start_loc.dtype == torch.int32
+        rc = 2
+        if ATTN_TC:
+            rc = L.gllm_attn_prefill_tc(_p(q), q.stride(0), _p(out), _p(k_cache), _p(v_cache), pages, _p(block_table),
+                                        _p(seq_lens), _p(query_start_loc), n_prefill, num_decode_seqs, max_q_len,
+                                        max_blocks, hq, hkv, d, page_size, float(scale), ATTN_TC_KV, st)
+            if rc != 2:                     # 2 = shape outside the tcgen05 kernel's envelope -> mma.sync kernel
+                check(rc, "attn_prefill_tc")
+                _count()
+                return out
         rc = L.gllm_attn_prefill(_p(q), q.stride(0), _p(out), _p(k_cache), _p(v_cache), pages, _p(block_table),
                                  _p(seq_lens), _p(query_start_loc), n_prefill, num_decode_seqs, max_q_len,
                                  max_blocks, hq, hkv, d, page_size, float(scale), st)

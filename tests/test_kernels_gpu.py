@@ -1,5 +1,6 @@
 """sm_100a kernels vs the PyTorch fp32 oracle (runs on the B200 box: `pytest -m gpu`)."""
 import math
+import os
 
 import pytest
 import torch
@@ -192,6 +193,27 @@ def test_attn_prefill_and_mixed(hq, hkv, d):
     # decode seqs first, then prefill chunks (some with prefix/chunk context)
     seq_lens = [7, 130, 40, 300, 129, 64, 1024]
     q_lens = [1, 1, 40, 100, 129, 3, 513]
+    nd = 2
+    q, kc, vc, bt, sl, qsl = _make_paged(seq_lens, q_lens, hq, hkv, d, 16, _dev(), seed=1)
+    scale = 1.0 / math.sqrt(d)
+    o = sm100.paged_attention(q, kc, vc, bt, sl, qsl, scale, hq, d, nd, len(seq_lens), max(q_lens), max(seq_lens))
+    torch.cuda.synchronize()
+    o_ref = ref.paged_attention(q, kc, vc, bt, sl, qsl, scale, hq, d)
+    assert torch.isfinite(o.float()).all()
+    assert _rel_err(o, o_ref) < 1e-2, _rel_err(o, o_ref)
+
+
+@pytest.mark.skipif(os.environ.get("GLLM_ATTN_TC", "0") != "1",
+                    reason="tcgen05 prefill attention is opt-in until validated on hardware (GLLM_ATTN_TC=1)")
+@pytest.mark.parametrize("kv_tile", [128, 64])
+@pytest.mark.parametrize("hq,hkv,d", [(32, 8, 128), (8, 8, 128), (28, 4, 128), (16, 2, 64)])
+def test_prefill_attention_tc(hq, hkv, d, kv_tile, monkeypatch):
+    """tcgen05 / TMEM prefill kernel vs the fp32 oracle: ragged chunks, prefix context, page-boundary cases."""
+    from gllm_b200.ops import sm100
+    monkeypatch.setattr(sm100, "ATTN_TC", True)
+    monkeypatch.setattr(sm100, "ATTN_TC_KV", kv_tile)
+    seq_lens = [7, 130, 40, 300, 129, 64, 1024, 257]
+    q_lens = [1, 1, 40, 100, 129, 3, 513, 257]
     nd = 2
     q, kc, vc, bt, sl, qsl = _make_paged(seq_lens, q_lens, hq, hkv, d, 16, _dev(), seed=1)
     scale = 1.0 / math.sqrt(d)

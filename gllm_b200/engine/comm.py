@@ -151,7 +151,27 @@ class Comm:
             out.append(pickle.loads(self.tok_in.recv()))
         return out
 
-    def close(self):
+    def close(self, unlink_all: bool = False):
+        """Close every socket. `unlink_all` (front-end, after the workers are gone) also removes the ipc socket
+        files of the whole engine instance: a worker that was terminated never gets to unlink its own."""
         for s in [self.sock_fe_in, self.sock_fe_out, self.batch_in, self.tok_in, self.tok_out, *self.batch_out]:
             if s is not None:
                 s.close(0)
+        self.sock_fe_in = self.sock_fe_out = self.batch_in = self.tok_in = self.tok_out = None
+        self.batch_out = []
+        if self.tcp_host is None and self.base.startswith("ipc://"):
+            import glob
+            root = self.base[len("ipc://"):]
+            if unlink_all:
+                paths = glob.glob(root + "_*")
+            elif self.frontend:
+                paths = [f"{root}_fe_out_0"]
+            elif self.rank == 0:
+                paths = [f"{root}_fe_req_0", f"{root}_tok_0"]
+            else:
+                paths = [f"{root}_batch_{self.rank}"]          # the endpoints this process bound
+            for path in paths:
+                try:
+                    os.unlink(path)
+                except OSError:
+                    pass

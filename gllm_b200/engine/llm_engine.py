@@ -396,21 +396,22 @@ class LLM:
 
     def shutdown(self):
         if self.worker is not None:
-            if self.is_external and self.worker.rank == 0:
-                pass
             self.worker.shutdown()
-        if self.comm is not None:
+        comm, self.comm = self.comm, None
+        if comm is not None:
             try:
-                self._post(IPCPackage(control_cmd=("stop",)))
-                time.sleep(0.05)
+                if self.worker is None:
+                    comm.send_frontend(IPCPackage(control_cmd=("stop",)))
+                    time.sleep(0.05)
             except Exception:  # noqa: BLE001
                 pass
-            self.comm.close()
         for p in self.procs:
             p.join(timeout=2)
             if p.is_alive():
                 p.terminate()
         self.procs = []
+        if comm is not None:
+            comm.close(unlink_all=True)   # after the workers are gone: nobody is left to re-create the ipc files
 
     def __del__(self):
         try:

@@ -6,6 +6,24 @@ import pytest
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
 
+_SCRATCH = []
+
+
+def scratch_dir(prefix: str) -> str:
+    """Temp directory for model files written by a test; everything is removed when the session ends
+    (`tempfile.mkdtemp` alone leaks one directory per test run)."""
+    import tempfile
+    if not _SCRATCH:
+        _SCRATCH.append(tempfile.mkdtemp(prefix="gllm_b200_pytest_"))
+    return tempfile.mkdtemp(prefix=prefix, dir=_SCRATCH[0])
+
+
+def pytest_sessionfinish(session, exitstatus):
+    import shutil
+    while _SCRATCH:
+        shutil.rmtree(_SCRATCH.pop(), ignore_errors=True)
+
+
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: test needs a CUDA device (run on the B200 box)")
 

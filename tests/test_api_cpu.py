@@ -1,7 +1,7 @@
 """OpenAI-API contract tests on CPU with fastapi.testclient: routes, SSE framing, usage, errors, metrics."""
+from conftest import scratch_dir
 import json
 import os
-import tempfile
 
 import pytest
 import torch
@@ -25,7 +25,7 @@ def _make_model_dir():
     cfg = LlamaConfig(hidden_size=64, intermediate_size=128, num_hidden_layers=2, num_attention_heads=2,
                       num_key_value_heads=2, vocab_size=len(words), max_position_embeddings=256, eos_token_id=2,
                       bos_token_id=1)
-    d = tempfile.mkdtemp(prefix="gllm_b200_api_")
+    d = scratch_dir("gllm_b200_api_")
     LlamaForCausalLM(cfg).eval().float().save_pretrained(d, safe_serialization=True)
     fast.save_pretrained(d)
     return d

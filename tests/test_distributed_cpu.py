@@ -1,10 +1,10 @@
 """Multi-process plumbing on CPU (gloo): TP, PP, PP x TP and EP layouts must reproduce the single-process
 tokens of the same model (same global weights sharded through the loader)."""
+from conftest import scratch_dir
 import json
 import os
 import subprocess
 import sys
-import tempfile
 
 import pytest
 
@@ -12,7 +12,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def _run(pp, tp, arch="Qwen3ForCausalLM", method="chunked_prefill", port=29811):
-    out = tempfile.mktemp(suffix=".json")
+    out = os.path.join(scratch_dir("gllm_b200_f_"), "f" + ".json")
     env = dict(os.environ, PYTHONPATH=ROOT, GLLM_B200_LOG="WARNING")
     script = os.path.join(ROOT, "tests", "mp_engine_cpu.py")
     n = pp * tp

@@ -1,7 +1,7 @@
 """Greedy-decode token-exact match against HuggingFace transformers on tiny random models (CPU, fp32),
 through the full engine: scheduler, chunked prefill, paged KV, prefix cache, loader."""
+from conftest import scratch_dir
 import os
-import tempfile
 
 import pytest
 import torch
@@ -10,7 +10,7 @@ transformers = pytest.importorskip("transformers")
 
 
 def _save(model):
-    d = tempfile.mkdtemp(prefix="gllm_b200_test_")
+    d = scratch_dir("gllm_b200_test_")
     model.save_pretrained(d, safe_serialization=True)
     return d
 

@@ -1,10 +1,10 @@
 """Multimodal request path through the OpenAI API on CPU: image_url (data URL) parsing, processor call (a small
 stand-in for the HF `AutoProcessor`, which needs real model files), M-RoPE position computation, pixel payload to
 the engine, vision tower + DeepStack in the forward. Text-only requests on the same server still work."""
+from conftest import scratch_dir
 import base64
 import io
 import json
-import tempfile
 
 import numpy as np
 import pytest
@@ -70,7 +70,7 @@ def _make_vl_dir():
                   deepstack_visual_indexes=[0, 1], in_channels=3)
     cfg = Qwen3VLConfig(text_config=text, vision_config=vision, image_token_id=IMG, video_token_id=VID,
                         vision_start_token_id=VSTART, tie_word_embeddings=False)
-    d = tempfile.mkdtemp(prefix="gllm_b200_vlapi_")
+    d = scratch_dir("gllm_b200_vlapi_")
     Qwen3VLForConditionalGeneration(cfg).eval().float().save_pretrained(d, safe_serialization=True)
     fast.save_pretrained(d)
     return d

@@ -1,11 +1,11 @@
 """Spawned-worker mode (front-end process + ZeroMQ + one worker process per rank) and the HTTP server as a
 real subprocess driven by the serving benchmark client — all on CPU."""
+from conftest import scratch_dir
 import json
 import os
 import socket
 import subprocess
 import sys
-import tempfile
 import time
 
 import pytest
@@ -37,7 +37,7 @@ if __name__ == "__main__":
     print("SPAWN_OK")
     llm.shutdown()
 """
-    f = tempfile.mktemp(suffix=".py")
+    f = os.path.join(scratch_dir("gllm_b200_f_"), "f" + ".py")
     open(f, "w").write(code)
     r = subprocess.run([sys.executable, f], capture_output=True, text=True, timeout=240,
                        env=dict(os.environ, GLLM_B200_LOG="WARNING"))
@@ -47,7 +47,7 @@ if __name__ == "__main__":
 def test_server_subprocess_with_serving_benchmark():
     import requests
     port = _free_port()
-    cfg = tempfile.mkdtemp(prefix="gllm_b200_srv_")
+    cfg = scratch_dir("gllm_b200_srv_")
     from gllm_b200.models.presets import tiny
     with open(os.path.join(cfg, "config.json"), "w") as f:
         json.dump(tiny("Qwen3ForCausalLM", max_position_embeddings=2048), f)
@@ -66,7 +66,7 @@ def test_server_subprocess_with_serving_benchmark():
         else:
             srv.kill()
             raise AssertionError("server did not come up: " + srv.stdout.read()[-3000:])
-        out = tempfile.mktemp(suffix=".json")
+        out = os.path.join(scratch_dir("gllm_b200_f_"), "f" + ".json")
         r = subprocess.run([sys.executable, os.path.join(ROOT, "benchmarks", "benchmark_serving.py"), "--port",
                             str(port), "--num-prompts", "12", "--request-rate", "50", "--vocab-size", "500",
                             "--max-output-len", "8", "--save-result", out, "--goodput", "ttft:60000"],
@@ -121,7 +121,7 @@ if __name__ == "__main__":
     print("MULTINODE_OK")
     llm.shutdown()
 """
-    fs, fm = tempfile.mktemp(suffix="_s.py"), tempfile.mktemp(suffix="_m.py")
+    fs, fm = os.path.join(scratch_dir("gllm_b200_f_"), "f" + "_s.py"), os.path.join(scratch_dir("gllm_b200_f_"), "f" + "_m.py")
     open(fs, "w").write(slave)
     open(fm, "w").write(master)
     env = dict(os.environ, GLLM_B200_LOG="WARNING")
@@ -154,9 +154,26 @@ if __name__ == "__main__":
     llm.generate(tokens=[[5, 17, 99], [9] * 40], output_lens=[60, 60], ignore_eos=True)
     print("SHOULD_NOT_REACH")
 """
-    f = tempfile.mktemp(suffix=".py")
+    f = os.path.join(scratch_dir("gllm_b200_f_"), "f" + ".py")
     open(f, "w").write(code)
     env = dict(os.environ, GLLM_B200_LOG="WARNING", GLLM_FAULT_INJECT="1:5")
     r = subprocess.run([sys.executable, f], env=env, capture_output=True, text=True, timeout=240)
     assert r.returncode != 0 and "SHOULD_NOT_REACH" not in r.stdout, r.stdout[-1000:] + r.stderr[-2000:]
     assert "fault injected" in (r.stdout + r.stderr)
+
+
+def test_shutdown_removes_ipc_socket_files(tmp_path):
+    """Engine shutdown must not leak ipc socket files (workers that get terminated cannot unlink their own)."""
+    import glob
+    from gllm_b200.engine.comm import Comm, ipc_base
+    base = ipc_base()
+    root = base[len("ipc://"):]
+    fe = Comm(base, -1, 2, 0, frontend=True).init()
+    drv = Comm(base, 0, 2, 0).init()
+    peer = Comm(base, 1, 2, 0).init()
+    assert len(glob.glob(root + "_*")) >= 3
+    peer.close()
+    assert not glob.glob(root + "_batch_1")
+    drv.close()
+    fe.close(unlink_all=True)
+    assert glob.glob(root + "_*") == []

@@ -1,6 +1,6 @@
 """Qwen2.5-VL / Qwen3-VL / Qwen3-VL-MoE against HuggingFace on tiny random models (CPU, fp32): vision tower,
 placeholder merge, M-RoPE positions (chunked + interleaved), DeepStack, chunked prefill across an image."""
-import tempfile
+from conftest import scratch_dir
 
 import numpy as np
 import pytest
@@ -34,7 +34,7 @@ def _hf_greedy(model, ids, pix, grids, n):
 
 def _ours(model, ids, pix, grids, n, **kw):
     from gllm_b200 import LLM
-    d = tempfile.mkdtemp(prefix="gllm_b200_vl_")
+    d = scratch_dir("gllm_b200_vl_")
     model.save_pretrained(d, safe_serialization=True)
     args = dict(maxp=64, maxd=64, page_size=16, num_cpu_pages=96, model_max_length=320, log_stats=False)
     args.update(kw)

@@ -60,6 +60,8 @@ class LLM:
             assigned_layers = [int(x) for x in assigned_layers.split(",")]
         if isinstance(worker_ranks, str):
             worker_ranks = [int(x) for x in worker_ranks.split(",")]
+        from gllm_b200.utils import resolve_model_path
+        model_path = resolve_model_path(model_path)      # HF repo id -> local snapshot (under a file lock)
         self.cfg = EngineConfig(
             model_path=model_path, load_format=load_format, host=host or "0.0.0.0", master_addr=master_addr,
             master_port=master_port, zmq_port_base=zmq_port_base, launch_mode=launch_mode,
@@ -382,7 +384,8 @@ class LLM:
                 self.schedule(on_token)
             del self.finished[base:]
             print()
-            history.append({"role": "assistant", "content": "".join(text)})
+            from gllm_b200.utils.chat import process_response
+            _, history = process_response((self.loader.config.get("architectures") or [""])[0], "".join(text), history)
 
     # -------------------------------------------------------------------------------------------
     def send_control_command(self, cmd: tuple):

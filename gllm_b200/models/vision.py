@@ -15,6 +15,7 @@ from typing import List
 import torch
 import torch.nn.functional as F
 from torch import nn
+from gllm_b200.utils import clamp_overflow
 
 
 def _rotate_half(x):
@@ -188,6 +189,8 @@ class Qwen2_5_VisionTower(nn.Module):
         cu_full = _frame_cu_seqlens(grid)
         for i, blk in enumerate(self.blocks):
             x = blk(x, cu_full if i in self.fullatt else cu_win, cos, sin)
+            if x.dtype == torch.float16:     # fp16 checkpoints can overflow in the ViT residual stream
+                x = clamp_overflow(x)
         out = self.merger(x)
         return out[torch.argsort(widx)], []
 

@@ -371,3 +371,61 @@ def test_weight_sharding_round_trip(tp):
             parts = partition_layers(layers, pp)
             assert [i for p in parts for i in p] == list(range(layers)) and all(len(p) > 0 for p in parts)
     assert [len(p) for p in partition_layers(64, 4, [16, 16, 17, 15])] == [16, 16, 17, 15]
+
+
+# ---------------------------------------------------------------------------------------------------------
+# utils: chat post-processing, model path resolution, helpers
+# ---------------------------------------------------------------------------------------------------------
+def test_glm_process_response_plain_and_tool_call():
+    from gllm_b200.utils.chat import process_response
+    hist = [{"role": "user", "content": "hi"}]
+    content, h2 = process_response("ChatGLMModel", "\n hello there ", hist)
+    assert content == "hello there" and h2[-1] == {"role": "assistant", "metadata": "", "content": "hello there"}
+    assert len(hist) == 1                                           # input history is not mutated
+    tools = [{"role": "system", "content": "tools", "tools": [{"name": "get_weather"}]},
+             {"role": "user", "content": "weather?"}]
+    out = "get_weather\n```python\ntool_call(city='Paris', days=3)\n```"
+    content, h3 = process_response("ChatGLMModel", out, tools)
+    assert content == {"name": "get_weather", "parameters": {"city": "Paris", "days": 3}}
+    assert h3[-1]["metadata"] == "get_weather"
+    # model output is never evaluated: a call expression inside an argument stays unparsed text
+    content, _ = process_response("ChatGLMModel", "t\n```python\ntool_call(x=__import__('os').getcwd())\n```", tools)
+    assert isinstance(content["parameters"], str)
+    # without advertised tools the payload is passed through; other architectures append one assistant turn
+    content, _ = process_response("ChatGLMModel", "interpreter\nprint(1)", hist)
+    assert content == {"name": "interpreter", "content": "print(1)"}
+    content, h4 = process_response("Qwen3ForCausalLM", "plain", hist)
+    assert content == "plain" and h4[-1] == {"role": "assistant", "content": "plain"}
+
+
+def test_resolve_model_path(tmp_path):
+    from gllm_b200.utils import resolve_model_path
+    assert resolve_model_path("preset:tiny") == "preset:tiny"
+    assert resolve_model_path({"a": 1}) == {"a": 1}
+    assert resolve_model_path(str(tmp_path)) == str(tmp_path)
+    calls = []
+
+    def fake_download(repo, cache_dir=None, allow_patterns=None):
+        calls.append((repo, tuple(allow_patterns)))
+        return str(tmp_path / "snap")
+
+    assert resolve_model_path("Qwen/Qwen3-8B", cache_dir=str(tmp_path), _download=fake_download) == str(tmp_path / "snap")
+    assert calls and calls[0][0] == "Qwen/Qwen3-8B" and "*.safetensors" in calls[0][1]
+    with pytest.raises(FileNotFoundError):
+        resolve_model_path("/no/such/dir/model")
+
+
+def test_util_helpers():
+    import asyncio
+    import torch
+    from gllm_b200 import utils
+    assert utils.round_up(17, 16) == 32 and utils.round_down(17, 16) == 16 and utils.cdiv(17, 16) == 2
+    assert utils.dtype_bytes(torch.bfloat16) == 2
+    x = torch.tensor([1.0, float("inf"), float("-inf"), float("nan")], dtype=torch.float16)
+    y = utils.clamp_overflow(x)
+    assert torch.isfinite(y).all() and y[0] == 1 and y[1] > 6e4 and y[2] < -6e4
+    assert utils.async_tensor_h2d([1, 2, 3], torch.int32, "cpu").tolist() == [1, 2, 3]
+
+    async def run():
+        return await utils.make_async(lambda a, b=0: a + b)(2, b=3)
+    assert asyncio.run(run()) == 5

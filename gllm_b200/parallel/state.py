@@ -230,13 +230,55 @@ def pp_row_tiles(num_rows: int, min_rows: Optional[int] = None, max_tiles: int =
     return [(i * per, min((i + 1) * per, num_rows)) for i in range(n) if i * per < num_rows]
 
 
+def _pp_shard_rows(r0: int, r1: int):
+    """TP>1: instead of every TP rank of a stage shipping the same replicated [rows, H] tile to its peer in the
+    next stage (what the reference does: tp_size redundant copies), rank k ships only the k-th
+    1/tp slice of the tile and the receiving stage re-assembles it with one all-gather over its own TP group
+    (NVLink) — tp x fewer bytes on the inter-stage link, which is the slow one when stages sit on different nodes.
+    Small tiles (decode) keep the replicated send: one more collective would cost more than the bytes saved.
+    -> (a, b, per) = this rank's row range and the padded slice length, or None for a replicated tile."""
+    import os
+    tp = get_tp_size()
+    if tp == 1 or os.environ.get("GLLM_PP_SHARD", "1") != "1":
+        return None
+    if r1 - r0 < int(os.environ.get("GLLM_PP_SHARD_MIN_ROWS", "256")):
+        return None
+    per = -(-(r1 - r0) // tp)
+    a = min(r0 + get_tp_rank() * per, r1)
+    return a, min(a + per, r1), per
+
+
+PP_STATS = {"sharded_tiles": 0, "replicated_tiles": 0}   # stage-boundary tiles received by this rank
+
+
 def pp_send_tiled(tensors: List[torch.Tensor], dst: Optional[int] = None):
     dst = get_next_pp_rank() if dst is None else dst
     handles = []
     for r0, r1 in pp_row_tiles(tensors[0].shape[0]):
-        for t in tensors:
-            handles.append(dist.isend(t[r0:r1], dst))
+        sh = _pp_shard_rows(r0, r1)
+        a, b = (r0, r1) if sh is None else sh[:2]
+        if b > a:
+            for t in tensors:
+                handles.append(dist.isend(t[a:b], dst))
     return handles
+
+
+class _ShardedTileWork:
+    """`wait()`-compatible handle of one sharded tile: p2p receive of this rank's slice, then the all-gather that
+    rebuilds rows r0:r1 of `tensor` on every TP rank of the stage."""
+
+    def __init__(self, works, tensor: torch.Tensor, r0: int, r1: int, a: int, b: int, per: int):
+        self.works, self.tensor, self.r0, self.r1, self.a, self.b, self.per = works, tensor, r0, r1, a, b, per
+
+    def wait(self):
+        for w in self.works:
+            w.wait()
+        t = self.tensor
+        mine = torch.zeros(self.per, *t.shape[1:], dtype=t.dtype, device=t.device)
+        mine[: self.b - self.a].copy_(t[self.a:self.b])
+        full = torch.empty(get_tp_size() * self.per, *t.shape[1:], dtype=t.dtype, device=t.device)
+        dist.all_gather_into_tensor(full, mine, group=get_tp_group())
+        t[self.r0:self.r1].copy_(full[: self.r1 - self.r0])   # slice k of the tile sits at rows k*per.. of `full`
 
 
 def pp_recv_tiled(tensors: List[torch.Tensor], src: Optional[int] = None):
@@ -244,5 +286,13 @@ def pp_recv_tiled(tensors: List[torch.Tensor], src: Optional[int] = None):
     src = get_prev_pp_rank() if src is None else src
     out = []
     for r0, r1 in pp_row_tiles(tensors[0].shape[0]):
-        out.append((r0, r1, [dist.irecv(t[r0:r1], src) for t in tensors]))
+        sh = _pp_shard_rows(r0, r1)
+        if sh is None:
+            PP_STATS["replicated_tiles"] += 1
+            out.append((r0, r1, [dist.irecv(t[r0:r1], src) for t in tensors]))
+            continue
+        PP_STATS["sharded_tiles"] += 1
+        a, b, per = sh
+        out.append((r0, r1, [_ShardedTileWork([dist.irecv(t[a:b], src)] if b > a else [], t, r0, r1, a, b, per)
+                             for t in tensors]))
     return out

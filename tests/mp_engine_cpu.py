@@ -33,6 +33,10 @@ def main():
     if int(os.environ.get("RANK", "0")) == 0:
         with open(out, "w") as f:
             json.dump([s.token_ids for s in outs], f)
+    if os.environ.get("GLLM_TEST_PP_STATS"):      # per-rank evidence that the sharded stage transfer really ran
+        from gllm_b200.parallel import state as ps
+        with open(f"{out}.pp{os.environ.get('RANK', '0')}", "w") as f:
+            json.dump(ps.PP_STATS, f)
     llm.shutdown()
     if torch.distributed.is_initialized():
         torch.distributed.barrier()

@@ -23,6 +23,7 @@ def _run(pp, tp, arch="Qwen3ForCausalLM", method="chunked_prefill", port=29811):
                "--master-addr", "127.0.0.1", "--master-port", str(port), script, str(pp), str(tp), out, arch, method]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=300, env=env, cwd=ROOT)
     assert r.returncode == 0 and os.path.exists(out), r.stdout[-2000:] + r.stderr[-3000:]
+    _run.last_out = out
     with open(out) as f:
         return json.load(f)
 
@@ -61,3 +62,17 @@ def test_tp2_async_lookahead_matches_single(single, monkeypatch):
     the peer rank over the packed ZeroMQ frame and every rank feeds from its own sampler output."""
     monkeypatch.setenv("GLLM_TEST_ASYNC", "1")
     assert _run(1, 2, port=29881) == single
+
+
+def test_pp2_tp2_sharded_stage_transfer_matches_single(single, monkeypatch):
+    """PP x TP: each TP rank ships only its 1/tp slice of a stage-boundary tile and the next stage all-gathers
+    it (uneven slices, several tiles per micro-batch, decode steps stay replicated)."""
+    monkeypatch.setenv("GLLM_PP_TILE_ROWS", "7")
+    monkeypatch.setenv("GLLM_PP_SHARD_MIN_ROWS", "3")
+    monkeypatch.setenv("GLLM_TEST_PP_STATS", "1")
+    assert _run(2, 2, port=29891) == single
+    stats = []
+    for rank in (2, 3):                                   # the second stage's TP ranks
+        with open(f"{_run.last_out}.pp{rank}") as f:
+            stats.append(json.load(f))
+    assert all(st["sharded_tiles"] > 0 and st["replicated_tiles"] > 0 for st in stats), stats

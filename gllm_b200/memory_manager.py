@@ -161,7 +161,11 @@ class PrefixMemoryManager(MemoryManager):
     def pre_allocate_page(self, seqs: List[Sequence]):
         ps = self.page_size
         for seq in seqs:
-            n_tok = seq.known_len   # a trailing lookahead placeholder is not hashable yet (async scheduling)
+            # (hot loop of every decode step: attribute reads instead of the Sequence properties)
+            n_tok = len(seq.token_ids) - (1 if seq.pending >= 0 else 0)   # a trailing lookahead placeholder is
+            have = len(seq.page_table)                                    # not hashable yet (async scheduling)
+            if n_tok % ps != 0 and (seq.scheduled_token_num + ps - 1) // ps <= have:
+                continue    # 15 of 16 decode steps: no page completed, none needed
             # a page completed by decode becomes cacheable
             if seq.computed_prompt and n_tok % ps == 0 and seq.page_table:
                 self._extend_hashes(seq, n_tok // ps)

@@ -187,7 +187,10 @@ class Scheduler:
                     seq.pending = -1
                 else:
                     seq.append(tok)
-                if seq.is_finish:
+                # == seq.is_finish (inlined: this loop runs once per sequence per step; the prompt is computed
+                # whenever an entry emits)
+                if (not seq.ignore_eos and tok in seq.finish_tokens) or \
+                        len(seq.token_ids) - seq.prompt_len >= seq.output_len:
                     out.free_ids.append(seq.seq_id)
                     if ahead:
                         seq.zombie = True

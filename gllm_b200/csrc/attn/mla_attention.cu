@@ -330,10 +330,10 @@ GLLM_EXPORT int gllm_mla_attention(const void* q, void* out, const void* cache, 
   p.max_blocks = max_blocks; p.H = H; p.page_size = page_size;
   p.num_splits = num_splits < 1 ? 1 : num_splits;
   p.scale_log2 = scale * 1.4426950408889634f;
-  static bool configured = false;
-  if (!configured) {
+  static PerDeviceOnce configured;
+  if (configured.need()) {
     CUDA_CHECK_RET(cudaFuncSetAttribute(mla_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMlaSmem));
-    configured = true;
+    configured.done();
   }
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   dim3 grid((H + 15) / 16, tokens, p.num_splits);

@@ -547,10 +547,10 @@ template <int D>
 static int launch_decode(const CUtensorMap& tk, const CUtensorMap& tv, const AttnParams& p, int num_seqs,
                          cudaStream_t st) {
   using SM = AttnSmem<D>;
-  static bool configured = false;
-  if (!configured) {
+  static PerDeviceOnce configured;
+  if (configured.need()) {
     CUDA_CHECK_RET(cudaFuncSetAttribute(attn_decode_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::kBytes));
-    configured = true;
+    configured.done();
   }
   dim3 grid(p.Hkv * (p.G / p.GP), num_seqs, p.num_splits);
   CUDA_CHECK_RET(launch_pdl(attn_decode_kernel<D>, grid, dim3(kAttnThreads), SM::kBytes, st, tk, tv, p));
@@ -561,10 +561,10 @@ template <int D>
 static int launch_prefill(const CUtensorMap& tk, const CUtensorMap& tv, const AttnParams& p, int num_seqs,
                           int max_q_len, cudaStream_t st) {
   using SM = AttnSmem<D>;
-  static bool configured = false;
-  if (!configured) {
+  static PerDeviceOnce configured;
+  if (configured.need()) {
     CUDA_CHECK_RET(cudaFuncSetAttribute(attn_prefill_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::kBytes));
-    configured = true;
+    configured.done();
   }
   const int toks_per_tile = 64 / p.GP;
   dim3 grid((max_q_len + toks_per_tile - 1) / toks_per_tile, num_seqs, p.Hkv * (p.G / p.GP));

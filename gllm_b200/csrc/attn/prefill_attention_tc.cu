@@ -395,11 +395,11 @@ template <int D, int KV>
 static int launch_prefill_tc(const CUtensorMap& tk, const CUtensorMap& tv, const TcAttnParams& p, int num_seqs,
                              int max_q_len, cudaStream_t st) {
   using SM = TcSmem<D, KV>;
-  static bool configured = false;
-  if (!configured) {
+  static PerDeviceOnce configured;
+  if (configured.need()) {
     CUDA_CHECK_RET(cudaFuncSetAttribute(attn_prefill_tc_kernel<D, KV>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         SM::kBytes));
-    configured = true;
+    configured.done();
   }
   const int toks_per_tile = kTcRows / p.GP;
   dim3 grid((max_q_len + toks_per_tile - 1) / toks_per_tile, num_seqs, p.Hkv * (p.G / p.GP));

@@ -103,10 +103,10 @@ GLLM_EXPORT int gllm_umma_mn_probe(const void* A, const void* Bt, void* D, int l
   p.lbo16 = lbo16; p.sbo16 = sbo16; p.k_adv16 = k_adv16; p.n_chunk_bytes = n_chunk_bytes;
   p.b_major = b_major; p.split_n = split_n;
   constexpr int smem = 32768 + 1024 + 256;
-  static bool configured = false;
-  if (!configured) {
+  static PerDeviceOnce configured;
+  if (configured.need()) {
     CUDA_CHECK_RET(cudaFuncSetAttribute(umma_mn_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    configured = true;
+    configured.done();
   }
   umma_mn_probe_kernel<<<1, 128, smem, reinterpret_cast<cudaStream_t>(stream)>>>(ta, tb, p);
   CUDA_CHECK_RET(cudaGetLastError());

@@ -97,6 +97,19 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
   return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
 }
 
+// `cudaFuncSetAttribute` is per DEVICE: a launcher remembers, per kernel instantiation, on which devices the
+// dynamic shared memory opt-in has been done (one process normally drives one GPU, but tests and tools may not).
+struct PerDeviceOnce {
+  unsigned long long mask = 0;   // devices 0..63
+  static unsigned long long bit() {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    return 1ull << (dev & 63);
+  }
+  bool need() const { return (__atomic_load_n(&mask, __ATOMIC_ACQUIRE) & bit()) == 0; }
+  void done() { __atomic_fetch_or(&mask, bit(), __ATOMIC_RELEASE); }
+};
+
 inline int num_sms() {
   static int n = 0;
   if (n == 0) {

@@ -454,12 +454,12 @@ template <int BN, int EPI>
 static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p,
                        cudaStream_t stream) {
   using Cfg = GemmCfg<BN>;
-  static bool configured = false;
+  static PerDeviceOnce configured;
   auto kern = gemm_bf16_kernel<BN, EPI>;
-  if (!configured) {
+  if (configured.need()) {
     CUDA_CHECK_RET(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         Cfg::kSmemBytes));
-    configured = true;
+    configured.done();
   }
   const int num_m = (p.M + kBlockM - 1) / kBlockM;
   const int num_n = (p.N + BN - 1) / BN;

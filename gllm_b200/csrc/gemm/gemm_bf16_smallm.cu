@@ -354,10 +354,10 @@ GLLM_EXPORT int gllm_gemm_smallm(const void* A, int64_t lda, const void* W, int6
   CUtensorMap tw, tx;
   if (make_tmap_2d(&tw, W, N, K, ldw * 2, kWTile, kBK, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16)) return 1;
   if (make_tmap_2d(&tx, A, M, K, lda * 2, p.BT, kBK, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16)) return 1;
-  static bool configured = false;
-  if (!configured) {
+  static PerDeviceOnce configured;
+  if (configured.need()) {
     CUDA_CHECK_RET(cudaFuncSetAttribute(gemm_smallm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    configured = true;
+    configured.done();
   }
   const int units = num_n * p.S;
   const int grid = units < sms ? units : sms;

@@ -257,10 +257,10 @@ GLLM_EXPORT int gllm_gemm_fp8_block(const void* A8, const void* a_s, const void*
   p.bias = reinterpret_cast<const __nv_bfloat16*>(bias);
   p.tile_expert = nullptr; p.num_m_tiles_ptr = nullptr; p.n_per_expert = 0; p.ws_stride_e = 0; p.silu = 0;
   constexpr int smem_bytes = kFStages * (kFBM * kFBK + kFBN * kFBK) + 1024 + 256;
-  static bool configured = false;
-  if (!configured) {
+  static PerDeviceOnce configured;
+  if (configured.need()) {
     CUDA_CHECK_RET(cudaFuncSetAttribute(gemm_fp8_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-    configured = true;
+    configured.done();
   }
   const int tiles = ((M + kFBM - 1) / kFBM) * ((N + kFBN - 1) / kFBN);
   const int grid = tiles < num_sms() ? tiles : num_sms();

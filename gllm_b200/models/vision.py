@@ -30,12 +30,56 @@ def _apply_rope(q, k, cos, sin):
     return (q * cos + _rotate_half(q) * sin).to(dt), (k * cos + _rotate_half(k) * sin).to(dt)
 
 
+# ------------------------------------------------------------------------------------------------
+# tensor parallelism inside the towers (reference: QKVParallel + all_gather_interleave in
+# gllm/models/qwen2_5_vl.py:160-239). Here: attention heads and the MLP intermediate dimension
+# are split over the TP group, the two row-parallel projections of a block end in an all-reduce; patch embedding,
+# position tables and the mergers stay replicated (small). `GLLM_VISION_TP=0` keeps the whole tower replicated.
+# ------------------------------------------------------------------------------------------------
+def vision_tp(heads: int, inter: int):
+    """-> (rank, size) the tower is sharded over; (0, 1) when not distributed or the shapes do not divide."""
+    import os
+    from gllm_b200.parallel import state as ps
+    st = ps.get_state()
+    if st.tp_size > 1 and os.environ.get("GLLM_VISION_TP", "1") == "1" and heads % st.tp_size == 0 \
+            and inter % st.tp_size == 0:
+        return st.tp_rank, st.tp_size
+    return 0, 1
+
+
+class _ColLinear(nn.Linear):
+    """Output features sharded over the TP group (`tp_kind` tells the weight loader how to slice)."""
+    tp_kind = "col"
+
+    def __init__(self, in_f, out_f, tp, bias=True):
+        super().__init__(in_f, out_f // tp[1], bias=bias)
+        self.tp = tp
+
+
+class _RowLinear(nn.Linear):
+    """Input features sharded; partial products are summed over the TP group, the (replicated) bias is added once."""
+    tp_kind = "row"
+
+    def __init__(self, in_f, out_f, tp, bias=True):
+        super().__init__(in_f // tp[1], out_f, bias=bias)
+        self.tp = tp
+
+    def forward(self, x):
+        y = F.linear(x, self.weight)
+        if self.tp[1] > 1:
+            from gllm_b200.parallel import state as ps
+            y = ps.tp_all_reduce(y)
+        return y if self.bias is None else y + self.bias
+
+
 class VisionAttention(nn.Module):
-    def __init__(self, dim: int, num_heads: int):
+    def __init__(self, dim: int, num_heads: int, tp=(0, 1)):
         super().__init__()
-        self.num_heads = num_heads
-        self.qkv = nn.Linear(dim, dim * 3, bias=True)
-        self.proj = nn.Linear(dim, dim)
+        self.num_heads = num_heads // tp[1]            # heads of this rank
+        self.qkv = _ColLinear(dim, dim * 3, tp)
+        self.qkv.tp_kind = "qkv"                       # rows are [3][heads][head_dim]: slice the heads axis
+        self.qkv.total_heads = num_heads
+        self.proj = _RowLinear(dim, dim, tp)
 
     def forward(self, x, cu_seqlens: List[int], cos, sin):
         s = x.shape[0]
@@ -102,22 +146,22 @@ class _PatchEmbed(nn.Module):
 
 
 class _SwiGLU(nn.Module):
-    def __init__(self, dim, inter):
+    def __init__(self, dim, inter, tp=(0, 1)):
         super().__init__()
-        self.gate_proj = nn.Linear(dim, inter, bias=True)
-        self.up_proj = nn.Linear(dim, inter, bias=True)
-        self.down_proj = nn.Linear(inter, dim, bias=True)
+        self.gate_proj = _ColLinear(dim, inter, tp)
+        self.up_proj = _ColLinear(dim, inter, tp)
+        self.down_proj = _RowLinear(inter, dim, tp)
 
     def forward(self, x):
         return self.down_proj(F.silu(self.gate_proj(x)) * self.up_proj(x))
 
 
 class _Block25(nn.Module):
-    def __init__(self, dim, heads, inter):
+    def __init__(self, dim, heads, inter, tp=(0, 1)):
         super().__init__()
         self.norm1, self.norm2 = RMSNorm(dim), RMSNorm(dim)
-        self.attn = VisionAttention(dim, heads)
-        self.mlp = _SwiGLU(dim, inter)
+        self.attn = VisionAttention(dim, heads, tp)
+        self.mlp = _SwiGLU(dim, inter, tp)
 
     def forward(self, x, cu, cos, sin):
         x = x + self.attn(self.norm1(x), cu, cos, sin)
@@ -146,7 +190,9 @@ class Qwen2_5_VisionTower(nn.Module):
         self.head_dim = dim // heads
         self.patch_embed = _PatchEmbed(vc.get("in_channels", vc.get("in_chans", 3)), vc.get("temporal_patch_size", 2),
                                        self.patch_size, dim, bias=False)
-        self.blocks = nn.ModuleList([_Block25(dim, heads, vc["intermediate_size"]) for _ in range(vc["depth"])])
+        self.tp = vision_tp(heads, vc["intermediate_size"])
+        self.blocks = nn.ModuleList([_Block25(dim, heads, vc["intermediate_size"], self.tp)
+                                     for _ in range(vc["depth"])])
         self.merger = _Merger25(vc["out_hidden_size"], dim, self.merge)
         self.to(device=device, dtype=dtype)
 
@@ -199,10 +245,10 @@ class Qwen2_5_VisionTower(nn.Module):
 # Qwen3-VL
 # ------------------------------------------------------------------------------------------------
 class _MLP3(nn.Module):
-    def __init__(self, dim, inter, act):
+    def __init__(self, dim, inter, act, tp=(0, 1)):
         super().__init__()
-        self.linear_fc1 = nn.Linear(dim, inter, bias=True)
-        self.linear_fc2 = nn.Linear(inter, dim, bias=True)
+        self.linear_fc1 = _ColLinear(dim, inter, tp)
+        self.linear_fc2 = _RowLinear(inter, dim, tp)
         self.tanh = "tanh" in act
 
     def forward(self, x):
@@ -210,11 +256,11 @@ class _MLP3(nn.Module):
 
 
 class _Block3(nn.Module):
-    def __init__(self, dim, heads, inter, act):
+    def __init__(self, dim, heads, inter, act, tp=(0, 1)):
         super().__init__()
         self.norm1, self.norm2 = nn.LayerNorm(dim, eps=1e-6), nn.LayerNorm(dim, eps=1e-6)
-        self.attn = VisionAttention(dim, heads)
-        self.mlp = _MLP3(dim, inter, act)
+        self.attn = VisionAttention(dim, heads, tp)
+        self.mlp = _MLP3(dim, inter, act, tp)
 
     def forward(self, x, cu, cos, sin):
         x = x + self.attn(self.norm1(x), cu, cos, sin)
@@ -246,7 +292,9 @@ class Qwen3VisionTower(nn.Module):
         self.pos_embed = nn.Embedding(vc["num_position_embeddings"], dim)
         self.side = int(vc["num_position_embeddings"] ** 0.5)
         act = vc.get("hidden_act", "gelu_pytorch_tanh")
-        self.blocks = nn.ModuleList([_Block3(dim, heads, vc["intermediate_size"], act) for _ in range(vc["depth"])])
+        self.tp = vision_tp(heads, vc["intermediate_size"])
+        self.blocks = nn.ModuleList([_Block3(dim, heads, vc["intermediate_size"], act, self.tp)
+                                     for _ in range(vc["depth"])])
         self.merger = _Merger3(dim, vc["out_hidden_size"], self.merge, False)
         self.deepstack_idx = list(vc.get("deepstack_visual_indexes", []) or [])
         self.deepstack_merger_list = nn.ModuleList(
@@ -292,6 +340,30 @@ class Qwen3VisionTower(nn.Module):
         return self.merger(x), deep
 
 
+def shard_vision_param(mod: nn.Module, pname: str, full: torch.Tensor) -> torch.Tensor:
+    """This rank's slice of a full checkpoint tensor for parameter `pname` ("weight" / "bias") of `mod`."""
+    kind = getattr(mod, "tp_kind", None)
+    rank, size = getattr(mod, "tp", (0, 1))
+    if kind is None or size == 1:
+        return full
+    if kind == "col":
+        n = full.shape[0] // size
+        return full[rank * n:(rank + 1) * n]
+    if kind == "row":
+        if pname == "bias":
+            return full
+        n = full.shape[1] // size
+        return full[:, rank * n:(rank + 1) * n]
+    if kind == "qkv":      # rows are [3][heads][head_dim]
+        heads = mod.total_heads
+        hl = heads // size
+        v = full.view(3, heads, full.shape[0] // (3 * heads), *full.shape[1:])
+        return v[:, rank * hl:(rank + 1) * hl].reshape(-1, *full.shape[1:])
+    raise ValueError(kind)
+
+
 def load_vision_weights(tower: nn.Module, reader, prefix: str = "visual."):
-    for name, p in tower.named_parameters():
-        p.data.copy_(reader.get(prefix + name).to(p.dtype))
+    for mname, mod in tower.named_modules():
+        for pname, p in mod.named_parameters(recurse=False):
+            name = f"{mname}.{pname}" if mname else pname
+            p.data.copy_(shard_vision_param(mod, pname, reader.get(prefix + name)).to(p.dtype))

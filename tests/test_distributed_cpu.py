@@ -76,3 +76,18 @@ def test_pp2_tp2_sharded_stage_transfer_matches_single(single, monkeypatch):
         with open(f"{_run.last_out}.pp{rank}") as f:
             stats.append(json.load(f))
     assert all(st["sharded_tiles"] > 0 and st["replicated_tiles"] > 0 for st in stats), stats
+
+
+@pytest.mark.parametrize("which", ["qwen2_5", "qwen3"])
+def test_vision_tower_tp2_matches_replicated(which):
+    """Heads / MLP-intermediate sharded vision towers == the replicated tower, on both ranks."""
+    out = os.path.join(scratch_dir("gllm_b200_f_"), "vision.json")
+    env = dict(os.environ, PYTHONPATH=ROOT, GLLM_B200_LOG="WARNING")
+    port = 29901 if which == "qwen2_5" else 29911
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr",
+           "127.0.0.1", "--master-port", str(port), os.path.join(ROOT, "tests", "mp_vision_tp_cpu.py"), out, which]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=300, env=env, cwd=ROOT)
+    assert r.returncode == 0 and os.path.exists(out), r.stdout[-2000:] + r.stderr[-3000:]
+    with open(out) as f:
+        res = json.load(f)
+    assert res["ok"], res

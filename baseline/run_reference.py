@@ -1,0 +1,96 @@
+"""Reference arm of bench.py: the UNMODIFIED reference (installed by baseline/install_reference.sh into
+baseline/_ref) driven through its own public API — `from gllm import LLM; LLM(...).generate(tokens=..)` — on the
+headline workload (Qwen3-8B shape, random-init weights via its `load_format="dummy"`, the same synthetic
+ShareGPT-shaped requests as our arm). Prints ONE JSON line on stdout; any failure is reported by the caller
+(bench.py) as {"impl": "reference", "unavailable": ...}.
+
+The reference spawns its own worker processes (one per GPU), so this runs in ONE process whatever N is; timing is
+wall clock around `generate` (the front-end process owns no CUDA context), K timed passes after W warm-up passes.
+"""
+import argparse
+import json
+import os
+import sys
+import tempfile
+import time
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+
+
+def qwen3_8b_dir(path):
+    """config.json + a stand-in tokenizer (one token per id; the benchmark feeds token ids) for Qwen3-8B."""
+    from tokenizers import Tokenizer, models, pre_tokenizers
+    from transformers import PreTrainedTokenizerFast
+    vocab = 151936
+    cfg = {"architectures": ["Qwen3ForCausalLM"], "model_type": "qwen3", "hidden_size": 4096,
+           "intermediate_size": 12288, "num_hidden_layers": 36, "num_attention_heads": 32, "num_key_value_heads": 8,
+           "head_dim": 128, "vocab_size": vocab, "max_position_embeddings": 40960, "rms_norm_eps": 1e-6,
+           "rope_theta": 1000000.0, "rope_scaling": None, "hidden_act": "silu", "tie_word_embeddings": False,
+           "attention_bias": False, "torch_dtype": "bfloat16", "bos_token_id": 151643, "eos_token_id": 151645}
+    os.makedirs(path, exist_ok=True)
+    with open(os.path.join(path, "config.json"), "w") as f:
+        json.dump(cfg, f)
+    with open(os.path.join(path, "generation_config.json"), "w") as f:
+        json.dump({"eos_token_id": [151645, 151643], "temperature": 0.6, "top_p": 0.95, "top_k": 20}, f)
+    tok = Tokenizer(models.WordLevel({f"t{i}": i for i in range(vocab)}, unk_token="t0"))
+    tok.pre_tokenizer = pre_tokenizers.Whitespace()
+    PreTrainedTokenizerFast(tokenizer_object=tok, unk_token="t0", eos_token="t151645",
+                            pad_token="t151643").save_pretrained(path)
+    return path
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--num-prompts", type=int, default=384)
+    ap.add_argument("--maxp", type=int, default=4096)
+    ap.add_argument("--maxd", type=int, default=1024)
+    ap.add_argument("--max-cuda-graph-bs", type=int, default=512)
+    ap.add_argument("--seed", type=int, default=0)
+    args = ap.parse_args()
+    sys.path.insert(0, ROOT)
+    from bench import synth_requests          # the same request generator as our arm
+    prompts, outs = synth_requests(args.num_prompts, 151936, args.seed)
+    from gllm import LLM                      # baseline/_ref on PYTHONPATH (set by bench.py)
+    model_dir = qwen3_8b_dir(tempfile.mkdtemp(prefix="gllm_ref_qwen3_8b_"))
+    llm = LLM(model_dir, load_format="dummy", tp_size=args.gpus, pp_size=1, maxp=args.maxp, maxd=args.maxd,
+              max_cuda_graph_bs=args.max_cuda_graph_bs, enable_prefix_caching=True,
+              schedule_method="chunked_prefill", master_port=str(int(os.environ.get("GLLM_REF_PORT", "18000"))),
+              zmq_port_base=int(os.environ.get("GLLM_REF_PORT", "18000")) + 1)
+
+    def one_pass():
+        t0 = time.perf_counter()
+        seqs = llm.generate(tokens=[list(p) for p in prompts], output_lens=list(outs), temperature=0.0, top_p=1.0,
+                            top_k=1)
+        dt = time.perf_counter() - t0
+        n_out = sum(len(s.token_ids) - s.prompt_len for s in seqs)
+        return dt, n_out
+
+    for _ in range(args.warmup):
+        one_pass()
+    tot_t = tot_tok = 0
+    for _ in range(args.steps):
+        dt, n = one_pass()
+        tot_t += dt
+        tot_tok += n
+    value = tot_tok / tot_t
+    print(json.dumps({
+        "impl": "reference", "metric": "output_tokens_per_s", "value": round(value, 2), "unit": "tokens/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": round(tot_t / args.steps * 1e3, 2), "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "bf16",
+        "data": "synthetic ShareGPT-shaped token ids (same generator and seed as our arm); random-init weights "
+                "(reference load_format=dummy)",
+        "timing": "wall clock around LLM.generate in the front-end process (workers are separate processes)",
+        "config": {"model": "Qwen3-8B", "num_prompts": args.num_prompts, "parallelism": f"tp{args.gpus}",
+                   "maxp": args.maxp, "maxd": args.maxd, "native_kernels": "vLLM 0.22 libraries of this image "
+                   "(the reference pins vLLM 0.11)"},
+        "e2e": {"value": round(value, 2), "unit": "tokens/s"}}), flush=True)
+    os._exit(0)      # the reference's daemon workers die with the front-end
+
+
+if __name__ == "__main__":
+    main()

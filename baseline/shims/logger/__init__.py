@@ -1,0 +1,28 @@
+"""Stand-in for the PyPI `logger` package the reference imports (`from logger import logger`,
+gllm/utils/__init__.py:27): a stdlib logger with one stream handler — the reference only re-formats the
+handlers (`init_logger`) and calls info / warning / error on it.
+
+Environment glue for this image (not part of the reference): the reference's `gllm/_C` is the vLLM `_C` extension;
+in the vLLM build installed here (0.22) the norm / rope / activation ops it calls (`torch.ops._C.rms_norm`, ...)
+live in a second library, `_C_stable_libtorch.abi3.so`, which the reference never loads. When
+GLLM_REF_PRELOAD_LIBS lists such libraries they are loaded here, i.e. in every process that imports the reference.
+"""
+import logging
+import os
+import sys
+
+logger = logging.getLogger("gllm")
+if not logger.handlers:
+    _h = logging.StreamHandler(sys.stderr)
+    logger.addHandler(_h)
+    logger.setLevel(os.environ.get("GLLM_REF_LOG", "INFO"))
+    logger.propagate = False
+
+_libs = [p for p in os.environ.get("GLLM_REF_PRELOAD_LIBS", "").split(":") if p]
+if _libs:
+    import torch
+    for _p in _libs:
+        try:
+            torch.ops.load_library(_p)
+        except Exception as _e:  # noqa: BLE001
+            logger.warning("could not preload %s: %r", _p, _e)

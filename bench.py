@@ -47,17 +47,67 @@ def parse():
 
 
 def reference_arm(args):
-    """The unmodified reference cannot be installed offline in this image: its setup.py downloads the
-    vLLM 0.11.0 wheel to extract the native kernels (setup.py:186-215), and it needs torch==2.8.0,
-    transformers<5 and the PyPI `logger` package — none available without a network."""
-    ref_dir = os.path.join(os.path.dirname(os.path.abspath(__file__)), "baseline", "_ref", "gllm")
-    why = "reference install impossible offline: setup.py must download the vLLM 0.11.0 wheel for its " \
-          "native kernels; also needs torch==2.8.0, transformers<5, PyPI 'logger' (see DESIGN.md)"
-    if os.path.isdir(ref_dir):
-        why = "baseline/_ref present but the reference's precompiled vLLM kernels are missing"
-    if int(os.environ.get("RANK", "0")) == 0:
-        print(json.dumps({"impl": "reference", "unavailable": why}))
-    return 0
+    """Run the unmodified reference (baseline/install_reference.sh -> baseline/_ref) through its own public API in
+    a subprocess (baseline/run_reference.py) and forward its JSON line. The reference pins vLLM 0.11 / torch 2.8 /
+    transformers < 5, this image has vLLM 0.22 / torch 2.11 / transformers 5: if its native ops or imports do not
+    line up on the box, the arm reports {"impl": "reference", "unavailable": <why>} and exits 0."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return 0          # the reference spawns its own per-GPU workers: only one front-end process
+    root = os.path.dirname(os.path.abspath(__file__))
+    ref_root = os.path.join(root, "baseline", "_ref")
+
+    def unavailable(why):
+        print(json.dumps({"impl": "reference", "unavailable": " ".join(str(why).split())[:600]}))
+        return 0
+
+    if not os.path.isfile(os.path.join(ref_root, "gllm", "llm_engine.py")):
+        return unavailable("baseline/_ref is not populated (run baseline/install_reference.sh; the reference's "
+                           "setup.py needs a vLLM wheel for its native kernels, see DESIGN.md)")
+    env = dict(os.environ)
+    for k in ("RANK", "LOCAL_RANK", "WORLD_SIZE", "MASTER_ADDR", "MASTER_PORT", "TORCHELASTIC_USE_AGENT_STORE",
+              "GROUP_RANK", "ROLE_RANK", "LOCAL_WORLD_SIZE", "TORCHELASTIC_RUN_ID"):
+        env.pop(k, None)  # the reference does its own rendezvous
+    env["PYTHONPATH"] = os.pathsep.join([ref_root, os.path.join(root, "baseline", "shims"),
+                                         env.get("PYTHONPATH", "")])
+    try:
+        import vllm
+        stable = os.path.join(os.path.dirname(vllm.__file__), "_C_stable_libtorch.abi3.so")
+        if os.path.exists(stable):
+            env["GLLM_REF_PRELOAD_LIBS"] = stable
+    except Exception:  # noqa: BLE001
+        pass
+    cmd = [sys.executable, os.path.join(root, "baseline", "run_reference.py"), "--gpus", str(args.gpus),
+           "--steps", str(args.steps), "--warmup", str(args.warmup), "--num-prompts", str(args.num_prompts),
+           "--maxp", str(args.maxp), "--maxd", str(args.maxd), "--max-cuda-graph-bs", str(args.max_cuda_graph_bs),
+           "--seed", str(args.seed)]
+    limit = int(os.environ.get("GLLM_REF_TIMEOUT", "1500"))
+    try:
+        # own process group: on a timeout the reference's spawned workers are taken down with the front-end
+        proc = subprocess.Popen(cmd, env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True,
+                                start_new_session=True)
+        import signal
+        timed_out = False
+        try:
+            out, err = proc.communicate(timeout=limit)
+        except subprocess.TimeoutExpired:
+            timed_out = True
+        finally:
+            try:       # always: worker processes the reference spawned must not keep GPU memory after the arm
+                os.killpg(proc.pid, signal.SIGKILL)
+            except (ProcessLookupError, PermissionError):
+                pass
+        if timed_out:
+            proc.communicate()
+            return unavailable(f"reference run exceeded {limit}s")
+    except Exception as e:  # noqa: BLE001
+        return unavailable(f"could not launch the reference: {e!r}")
+    for line in reversed(out.splitlines()):
+        if line.startswith("{") and '"impl": "reference"' in line:
+            print(line)
+            return 0
+    tail = (err.strip().splitlines() or out.strip().splitlines() or ["no output"])[-1]
+    return unavailable(f"reference failed on this image (vLLM 0.22 / torch 2.11 / transformers 5 instead of its "
+                       f"pinned 0.11 / 2.8 / <5): {tail}")
 
 
 def synth_requests(n, vocab, seed):

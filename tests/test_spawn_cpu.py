@@ -177,3 +177,24 @@ def test_shutdown_removes_ipc_socket_files(tmp_path):
     drv.close()
     fe.close(unlink_all=True)
     assert glob.glob(root + "_*") == []
+
+
+def test_offline_throughput_benchmark_and_batch_example():
+    """benchmarks/benchmark_throughput.py and examples/batch_inference.py end to end on a tiny dummy model
+    (reference: benchmarks/benchmark_throughput.py, examples/batch_inference.py)."""
+    cfg = scratch_dir("gllm_b200_tp_")
+    from gllm_b200.models.presets import tiny
+    with open(os.path.join(cfg, "config.json"), "w") as f:
+        json.dump(tiny("Qwen3ForCausalLM", max_position_embeddings=4096), f)
+    env = dict(os.environ, PYTHONPATH=ROOT, GLLM_B200_LOG="WARNING")
+    out = os.path.join(cfg, "throughput.json")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "benchmarks", "benchmark_throughput.py"), "--model-path", cfg,
+                        "--load-format", "dummy", "--num-prompts", "6", "--maxp", "64", "--maxd", "16",
+                        "--output-json", out], capture_output=True, text=True, timeout=240, env=env)
+    assert r.returncode == 0 and "Throughput:" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+    res = json.load(open(out))
+    assert res["num_prompts"] == 6 and res["output_tokens"] > 0 and res["output_tokens_per_s"] > 0
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "examples", "batch_inference.py"), "--model-path", cfg,
+                        "--load-format", "dummy", "--num-prompts", "4", "--output-len", "6"],
+                       capture_output=True, text=True, timeout=240, env=env)
+    assert r.returncode == 0 and "output tok/s" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]

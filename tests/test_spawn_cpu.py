@@ -198,3 +198,55 @@ def test_offline_throughput_benchmark_and_batch_example():
                         "--load-format", "dummy", "--num-prompts", "4", "--output-len", "6"],
                        capture_output=True, text=True, timeout=240, env=env)
     assert r.returncode == 0 and "output tok/s" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+def test_mmlu_pro_script_and_chat_clients_against_server():
+    """benchmarks/evaluate_MMLU_pro.py (local json dataset) and the example chat clients against a real server
+    process with a tokenizer + chat template (reference: benchmarks/evaluate_MMLU_pro.py, examples/client.py)."""
+    import requests
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from test_api_cpu import _make_model_dir
+    model = _make_model_dir()
+    data = scratch_dir("gllm_b200_mmlu_")
+    rows = [{"question": f"how are you w{i} ?", "options": ["hello", "world", "the", "a"], "answer": "ABCD"[i % 4],
+             "category": "math" if i % 2 else "law", "cot_content": ""} for i in range(8)]
+    with open(os.path.join(data, "test.json"), "w") as f:
+        json.dump(rows, f)
+    with open(os.path.join(data, "validation.json"), "w") as f:
+        json.dump(rows[:4], f)
+    port = _free_port()
+    env = dict(os.environ, PYTHONPATH=ROOT, GLLM_B200_LOG="WARNING")
+    srv = subprocess.Popen([sys.executable, "-m", "gllm_b200.entrypoints.api_server", "--model-path", model,
+                            "--port", str(port), "--host", "127.0.0.1", "--maxp", "64", "--maxd", "16",
+                            "--model-max-length", "250"], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT,
+                           text=True)
+    try:
+        for _ in range(120):
+            try:
+                if requests.get(f"http://127.0.0.1:{port}/health", timeout=1).status_code == 200:
+                    break
+            except Exception:  # noqa: BLE001
+                time.sleep(0.5)
+        else:
+            srv.kill()
+            raise AssertionError("server did not come up: " + srv.stdout.read()[-3000:])
+        r = subprocess.run([sys.executable, os.path.join(ROOT, "benchmarks", "evaluate_MMLU_pro.py"), "--data-dir", data,
+                            "--port", str(port), "--num-per-subject", "3", "--max-tokens", "4", "--workers", "2"],
+                           capture_output=True, text=True, timeout=240, env=env)
+        assert r.returncode == 0 and "overall" in r.stdout and "(6)" in r.stdout.splitlines()[-1], \
+            r.stdout[-2000:] + r.stderr[-2000:]
+        for extra in ([], ["--stream"]):     # examples/client.py: plain and SSE completions
+            r = subprocess.run([sys.executable, os.path.join(ROOT, "examples", "client.py"), "--port", str(port),
+                                "--prompt", "hello world how are you", "--max-tokens", "5", *extra],
+                               capture_output=True, text=True, timeout=120, env=env)
+            assert r.returncode == 0 and r.stdout.strip(), r.stdout[-1000:] + r.stderr[-2000:]
+        # examples/chat_client.py is interactive: one question, then EOF
+        r = subprocess.run([sys.executable, os.path.join(ROOT, "examples", "chat_client.py"), "--port", str(port)],
+                           input="hello world\n", capture_output=True, text=True, timeout=120, env=env)
+        assert r.returncode == 0, r.stdout[-1000:] + r.stderr[-2000:]
+    finally:
+        srv.terminate()
+        try:
+            srv.wait(timeout=10)
+        except Exception:  # noqa: BLE001
+            srv.kill()

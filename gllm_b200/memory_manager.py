@@ -167,7 +167,9 @@ class PrefixMemoryManager(MemoryManager):
             if n_tok % ps != 0 and (seq.scheduled_token_num + ps - 1) // ps <= have:
                 continue    # 15 of 16 decode steps: no page completed, none needed
             # a page completed by decode becomes cacheable
-            if seq.computed_prompt and n_tok % ps == 0 and seq.page_table:
+            # (a chunked recompute after a preemption can get here with the page not allocated yet: then the
+            # allocation loop below registers its hash)
+            if seq.computed_prompt and n_tok % ps == 0 and 0 < n_tok // ps <= have:
                 self._extend_hashes(seq, n_tok // ps)
                 h = seq.page_hashes[n_tok // ps - 1]
                 page = seq.page_table[n_tok // ps - 1]

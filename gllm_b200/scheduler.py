@@ -291,10 +291,36 @@ class Scheduler:
     def schedule_once(self) -> List["ScheduledSeq"]:
         if not self.can_schedule():
             return []
-        seqs = self.token_throttling() if self.schedule_method == "token_throttling" else self.chunked_prefill()
+        seqs = self._schedule()
+        if not seqs and not self.batch_running and not self.seqs_to_decode and self._break_prefill_stall():
+            seqs = self._schedule()
         if seqs:
             self.batch_running.append(seqs)
         return seqs
+
+    def _schedule(self) -> List["ScheduledSeq"]:
+        return self.token_throttling() if self.schedule_method == "token_throttling" else self.chunked_prefill()
+
+    def _break_prefill_stall(self) -> bool:
+        """Nothing is running, nothing could be scheduled, yet sequences are waiting: every free page is gone to
+        partially prefilled sequences (preempted sequences re-enter at the head of the queue, in front of a
+        half-prefilled one, so several of them can end up holding pages) and nobody can advance. Give back the
+        pages of waiting sequences from the tail of the queue — they are recomputed later — until the head has
+        room again. Returns whether anything was freed."""
+        if len(self.seqs_to_prefill) < 2:
+            return False
+        head, freed = self.seqs_to_prefill[0], False
+        for seq in reversed(self.seqs_to_prefill):
+            if seq is head:
+                break
+            if seq.page_table:
+                self.mm.free(seq)
+                seq.preempt()
+                self.num_preempt_seqs += 1
+                freed = True
+                if self.mm.get_num_free_pages() > self.num_kvthresh_pages:
+                    break
+        return freed
 
     def check_preempt(self, num_pages_to_allocate: int):
         preempted = []
@@ -355,8 +381,10 @@ class Scheduler:
         budget = self.maxp
         num_total_decode = self.get_num_decode_seqs()
         decode_budget = min(balanced_decode_budget(num_total_decode, self.pp_size, self.maxd), budget)
+        # split_pd: prefill has priority while there is KV headroom for it. (Strictly positive headroom: with
+        # free pages == threshold neither phase would be scheduled and the engine would stall.)
         if self.schedule_method == "split_pd" and self.seqs_to_prefill and \
-                self.mm.get_num_free_pages() >= self.num_kvthresh_pages:
+                kv_headroom_tokens(self.mm.get_num_free_pages(), self.num_kvthresh_pages, self.page_size) > 0:
             decode_budget = 0
         decode_batch = self.schedule_decode_batch(decode_budget)
         budget -= len(decode_batch)

@@ -1,0 +1,100 @@
+"""Property tests (hypothesis): random request streams through the real Scheduler + PrefixMemoryManager must
+keep the paged-KV bookkeeping consistent at every step (allocator / prefix-cache refcount and
+eviction invariants; scheduler budgets; abort and preemption paths)."""
+import random
+
+import pytest
+
+hypothesis = pytest.importorskip("hypothesis")
+from hypothesis import HealthCheck, given, settings, strategies as st  # noqa: E402
+
+from gllm_b200.memory_manager import PrefixMemoryManager  # noqa: E402
+from gllm_b200.scheduler import Scheduler  # noqa: E402
+from gllm_b200.sequence import Sequence  # noqa: E402
+
+PAGE = 4
+
+
+def check_invariants(mm: PrefixMemoryManager, live):
+    """live: sequences that may hold pages (running, waiting with cached prefix, ...)."""
+    holders = {}
+    for s in live:
+        assert len(set(s.page_table)) == len(s.page_table), "a sequence holds a page twice"
+        for p in s.page_table:
+            holders[p] = holders.get(p, 0) + 1
+    for p in range(mm.num_pages):
+        ref = mm.page_ref[p]
+        assert ref >= 0
+        assert ref == holders.get(p, 0), (p, ref, holders.get(p, 0))        # refcount == number of holders
+        assert mm.id_allocator.is_free(p) == (ref == 0), p                  # free list <=> nobody holds it
+    assert mm.get_num_free_pages() == mm.num_pages - len(holders)
+    for h, p in mm.hash2page.items():                                       # hash maps are mutually consistent
+        assert mm.page2hash[p] == h
+    # two sequences share a page only if they agree on every token up to the end of that page
+    owner = {}
+    for s in live:
+        for i, p in enumerate(s.page_table):
+            if p in owner and owner[p][0] is not s:
+                o, j = owner[p]
+                assert i == j and o.token_ids[:(i + 1) * PAGE] == s.token_ids[:(i + 1) * PAGE]
+            owner.setdefault(p, (s, i))
+
+
+@settings(max_examples=int(__import__("os").environ.get("GLLM_HYP_EXAMPLES", "60")), deadline=None, derandomize=not __import__("os").environ.get("GLLM_HYP_RANDOM"), suppress_health_check=[HealthCheck.too_slow])
+@given(seed=st.integers(0, 10 ** 6), n_req=st.integers(1, 14), pages=st.integers(10, 40),
+       method=st.sampled_from(["chunked_prefill", "token_throttling", "split_pd"]),
+       maxp=st.sampled_from([8, 16, 64]), abort_rate=st.sampled_from([0.0, 0.1]), pp=st.sampled_from([1, 2]))
+def test_random_streams_keep_kv_bookkeeping_consistent(seed, n_req, pages, method, maxp, abort_rate, pp):
+    rng = random.Random(seed)
+    mm = PrefixMemoryManager(pages, PAGE)
+    sch = Scheduler(mm, pp_size=pp, world_size=pp, schedule_method=method, maxd=6, maxp=maxp, minp=4, iterp=2,
+                    kvthresh=0.0, page_size=PAGE, log=False)
+    # prompts drawn from a few shared prefixes so that the prefix cache really gets hits and shared pages
+    stems = [[rng.randrange(50) for _ in range(rng.randrange(2, 14))] for _ in range(3)]
+    reqs = []
+    for i in range(n_req):
+        stem = rng.choice(stems)
+        toks = stem[:rng.randrange(1, len(stem) + 1)] + [rng.randrange(50) for _ in range(rng.randrange(0, 6))]
+        out = rng.randrange(1, 9)
+        if (len(toks) + out + PAGE - 1) // PAGE > pages - 1:
+            continue
+        reqs.append(Sequence(i, toks, [2], output_len=out, ignore_eos=True))
+    pending = list(reqs)
+    everyone = list(reqs)
+    produced = {}
+    inflight = []
+    for step in range(1200):
+        if pending and rng.random() < 0.5:
+            k = rng.randrange(1, len(pending) + 1)
+            sch.add_new_requests(pending[:k])
+            del pending[:k]
+        if abort_rate and rng.random() < abort_rate and everyone:
+            sch.add_abort_ids([rng.choice(everyone).seq_id])
+            out = sch.check_abort_seqs()
+        batch = sch.schedule_once()
+        check_invariants(mm, everyone)
+        if batch:
+            assert len(sch.batch_running) <= pp                              # <= pp micro-batches in flight
+            n_dec = next((i for i, e in enumerate(batch) if not e.is_decode), len(batch))
+            assert all(e.n == 1 and e.emits for e in batch[:n_dec])          # leading decode rows: one token each
+            assert len({e.seq.seq_id for e in batch}) == len(batch)          # a sequence appears once per batch
+            for e in batch:
+                need = (e.start + e.n + PAGE - 1) // PAGE
+                assert len(e.seq.page_table) >= need                         # KV room exists for what will run
+            inflight.append(batch)
+        if inflight and (len(inflight) == pp or not batch):
+            done = inflight.pop(0)
+            sch.add_next_tokens([rng.randrange(3, 50) for e in done if e.emits])
+            out = sch.process_output()
+            for sid, tok in zip(out.act_schedule_ids, out.next_tokens):
+                produced.setdefault(sid, []).append(tok)
+            check_invariants(mm, everyone)
+        if not pending and not sch.has_work():
+            break
+    assert not sch.has_work() and not pending, "engine did not drain"
+    for s in reqs:
+        assert not s.page_table                                              # everything was given back
+        if not s.is_abort:
+            assert len(produced.get(s.seq_id, [])) == s.output_len
+    assert mm.get_num_free_pages() == pages
+    check_invariants(mm, [])

@@ -98,3 +98,83 @@ def test_random_streams_keep_kv_bookkeeping_consistent(seed, n_req, pages, metho
             assert len(produced.get(s.seq_id, [])) == s.output_len
     assert mm.get_num_free_pages() == pages
     check_invariants(mm, [])
+
+
+def _tok(seq_id: int, pos: int) -> int:
+    """Deterministic stand-in for the model: the token at position `pos` of a sequence depends on nothing else,
+    so synchronous and lookahead scheduling must produce identical streams."""
+    return 3 + (seq_id * 7919 + pos * 104729) % 45
+
+
+def _drive(reqs_spec, pages, method, maxp, lookahead, arrivals, abort_plan):
+    """Emulates the driver loop of engine/worker.py (run_driver) around the real Scheduler."""
+    mm = PrefixMemoryManager(pages, PAGE)
+    sch = Scheduler(mm, pp_size=1, world_size=1, schedule_method=method, maxd=6, maxp=maxp, minp=4, iterp=2,
+                    kvthresh=0.0, page_size=PAGE, log=False)
+    reqs = [Sequence(i, list(t), [2], output_len=o, ignore_eos=True) for i, (t, o) in enumerate(reqs_spec)]
+    pending_reqs = list(reqs)
+    inflight = []            # launched batches whose tokens are not back yet (<= 2 with lookahead)
+    produced = {}
+    n_look = 0
+    for step in range(3000):
+        if pending_reqs and arrivals[step % len(arrivals)]:
+            sch.add_new_requests([pending_reqs.pop(0)])
+        if step in abort_plan and abort_plan[step] < len(reqs):
+            sch.add_abort_ids([abort_plan[step]])
+        sch.check_abort_seqs()
+        if lookahead and len(inflight) == 1:
+            look = sch.schedule_lookahead()
+            if look:
+                n_look += 1
+                inflight.append(look)
+        keep = 1 if (lookahead and len(inflight) == 2) else 0
+        while len(inflight) > keep:
+            done = inflight.pop(0)
+            sch.add_next_tokens([_tok(e.seq.seq_id, e.start + e.n) for e in done if e.emits])
+        while True:
+            out = sch.process_output()
+            if out is None:
+                break
+            for sid, tok in zip(out.act_schedule_ids, out.next_tokens):
+                produced.setdefault(sid, []).append(tok)
+        check_invariants(mm, reqs)
+        entries = sch.schedule_once()
+        if entries:
+            inflight.append(entries)
+        if not pending_reqs and not sch.has_work() and not inflight:
+            break
+    assert not pending_reqs and not sch.has_work() and not inflight, "engine did not drain"
+    assert mm.get_num_free_pages() == pages
+    for s in reqs:
+        assert not s.page_table and s.pending < 0 and not s.zombie
+    return reqs, produced, n_look
+
+
+@settings(max_examples=int(__import__("os").environ.get("GLLM_HYP_EXAMPLES", "60")), deadline=None,
+          derandomize=not __import__("os").environ.get("GLLM_HYP_RANDOM"), suppress_health_check=[HealthCheck.too_slow])
+@given(seed=st.integers(0, 10 ** 6), n_req=st.integers(1, 10), pages=st.integers(12, 48),
+       method=st.sampled_from(["chunked_prefill", "token_throttling"]), maxp=st.sampled_from([8, 16, 64]),
+       aborts=st.booleans())
+def test_lookahead_scheduling_equals_synchronous(seed, n_req, pages, method, maxp, aborts):
+    """Async (lookahead) scheduling — placeholder tokens, zombies, pages reserved one step ahead — must give every
+    request exactly the tokens the synchronous loop gives it and leave no page behind."""
+    rng = random.Random(seed)
+    spec = []
+    for _ in range(n_req):
+        toks = [rng.randrange(3, 50) for _ in range(rng.randrange(1, 18))]
+        out = rng.randrange(1, 12)
+        if (len(toks) + out + PAGE - 1) // PAGE <= pages - 2:
+            spec.append((toks, out))
+    arrivals = [rng.random() < 0.6 for _ in range(17)] + [True]
+    abort_plan = {rng.randrange(0, 40): rng.randrange(0, max(len(spec), 1)) for _ in range(2)} if aborts else {}
+    reqs_s, prod_s, _ = _drive(spec, pages, method, maxp, False, arrivals, abort_plan)
+    reqs_a, prod_a, n_look = _drive(spec, pages, method, maxp, True, arrivals, abort_plan)
+    for s, a in zip(reqs_s, reqs_a):
+        want = [_tok(s.seq_id, s.prompt_len + i) for i in range(s.output_len)]
+        if not s.is_abort:
+            assert prod_s.get(s.seq_id, []) == want
+        if not a.is_abort:
+            assert prod_a.get(a.seq_id, []) == want, (a.seq_id, prod_a.get(a.seq_id), want)
+        else:   # an aborted request may have streamed a prefix of its tokens, never anything else
+            got = prod_a.get(a.seq_id, [])
+            assert got == want[:len(got)]

@@ -3,11 +3,13 @@ keep the paged-KV bookkeeping consistent at every step (allocator 
 eviction invariants; scheduler budgets; abort and preemption paths)."""
 import random
 
+import numpy as np
 import pytest
 
 hypothesis = pytest.importorskip("hypothesis")
 from hypothesis import HealthCheck, given, settings, strategies as st  # noqa: E402
 
+from gllm_b200.input_data import build_batch  # noqa: E402
 from gllm_b200.memory_manager import PrefixMemoryManager  # noqa: E402
 from gllm_b200.scheduler import Scheduler  # noqa: E402
 from gllm_b200.sequence import Sequence  # noqa: E402
@@ -63,6 +65,7 @@ def test_random_streams_keep_kv_bookkeeping_consistent(seed, n_req, pages, metho
     everyone = list(reqs)
     produced = {}
     inflight = []
+    prev_arrays, bid = None, 0
     for step in range(1200):
         if pending and rng.random() < 0.5:
             k = rng.randrange(1, len(pending) + 1)
@@ -82,6 +85,20 @@ def test_random_streams_keep_kv_bookkeeping_consistent(seed, n_req, pages, metho
                 need = (e.start + e.n + PAGE - 1) // PAGE
                 assert len(e.seq.page_table) >= need                         # KV room exists for what will run
             inflight.append(batch)
+            # the incremental decode path of build_batch must equal a from-scratch build of the same entries
+            bid += 1
+            inc = build_batch(batch, PAGE, 64, bid, prev=prev_arrays if pp == 1 else None)
+            full = build_batch(batch, PAGE, 64, bid, prev=None)
+            for name in ("tokens", "positions", "slot_mapping", "seq_lens", "query_start_loc", "logits_idx",
+                         "temperature", "top_k", "top_p", "rep_penalty"):
+                assert np.array_equal(getattr(inc, name), getattr(full, name)), name
+            w = full.block_table.shape[1]
+            for r in range(len(batch)):   # compare the pages each row really uses
+                nblk = (int(full.seq_lens[r]) + PAGE - 1) // PAGE
+                assert np.array_equal(inc.block_table[r, :nblk], full.block_table[r, :nblk])
+            assert (inc.num_decode_seqs, inc.num_seqs, inc.num_tokens, inc.max_q_len, inc.max_seq_len) == \
+                (full.num_decode_seqs, full.num_seqs, full.num_tokens, full.max_q_len, full.max_seq_len)
+            prev_arrays = inc
         if inflight and (len(inflight) == pp or not batch):
             done = inflight.pop(0)
             sch.add_next_tokens([rng.randrange(3, 50) for e in done if e.emits])

@@ -15,6 +15,8 @@ from __future__ import annotations
 
 import os
 import pickle
+import struct
+import time
 import uuid
 from dataclasses import dataclass, field
 from typing import List, Optional
@@ -72,6 +74,7 @@ class Comm:
         self.batch_out: List[zmq.Socket] = []
         self.batch_in = None
         self.tok_in = self.tok_out = None
+        self.ring_w = self.ring_r = None       # shared-memory batch ring (driver writes, peers read)
 
     # addresses ---------------------------------------------------------------------------------
     def _addr(self, name: str, idx: int = 0, bind: bool = False) -> str:
@@ -92,16 +95,20 @@ class Comm:
             self.sock_fe_in = make_socket(self.ctx, L, self._addr("fe_out", bind=True), bind=True)
             return self
         tcp = self.tcp_host is not None
+        ring = self.use_shm_ring()
+        if ring:
+            self.init_ring()
         if self.rank == 0:
             self.sock_fe_in = make_socket(self.ctx, L, self._addr("fe_req", bind=True), bind=True)
             self.sock_fe_out = make_socket(self.ctx, P, self._addr("fe_out"), bind=False)
-            for r in range(1, self.world_size):
+            for r in range(1, self.world_size if not ring else 1):
                 # ipc: the peer binds its inbox and the driver connects; tcp: the driver binds, the peer connects
                 self.batch_out.append(make_socket(self.ctx, P, self._addr("batch", r, bind=tcp), bind=tcp))
             if self.output_rank != 0:
                 self.tok_in = make_socket(self.ctx, L, self._addr("tok", bind=True), bind=True)
         else:
-            self.batch_in = make_socket(self.ctx, L, self._addr("batch", self.rank, bind=not tcp), bind=not tcp)
+            if not ring:
+                self.batch_in = make_socket(self.ctx, L, self._addr("batch", self.rank, bind=not tcp), bind=not tcp)
             if self.rank == self.output_rank:
                 self.tok_out = make_socket(self.ctx, P, self._addr("tok"), bind=False)
         return self
@@ -117,29 +124,81 @@ class Comm:
         return out
 
     # driver -> peers -----------------------------------------------------------------------------
+    # batch channel: ZeroMQ PUSH/PULL per peer, or (GLLM_BATCH_TRANSPORT=shm, single node, x86-64) one
+    # shared-memory broadcast ring written once by the driver — see engine/shm_ring.py for the why
+    def use_shm_ring(self) -> bool:
+        import platform
+        return (self.tcp_host is None and self.world_size > 1 and self.base.startswith("ipc://")
+                and os.environ.get("GLLM_BATCH_TRANSPORT", "zmq") == "shm"
+                and platform.machine() in ("x86_64", "AMD64"))
+
+    def _ring_name(self) -> str:
+        return os.path.basename(self.base[len("ipc://"):]) + "_ring"
+
+    def init_ring(self):
+        from gllm_b200.engine import shm_ring
+        if self.rank == 0:
+            cap = int(os.environ.get("GLLM_SHM_RING_MB", "32")) << 20
+            self.ring_w = shm_ring.RingWriter(self._ring_name(), self.world_size - 1, cap)
+        else:
+            self.ring_r = shm_ring.RingReader(self._ring_name(), self.rank - 1)
+
+    @staticmethod
+    def _encode_batch(batch: BatchArrays) -> bytes:
+        """u32 header length | pickled header | pad to 16 | packed arrays — ONE buffer per batch. (Two-frame
+        zero-copy multipart sends cost ~35 % more per peer for the ~10 KB decode batches that dominate.)"""
+        hdr, bufs = batch.to_wire()
+        h = pickle.dumps(hdr, protocol=pickle.HIGHEST_PROTOCOL)
+        head = struct.pack("<I", len(h)) + h
+        return b"".join((head, b"\0" * (-len(head) % 16), memoryview(bufs[0])))
+
+    @staticmethod
+    def _decode_batch(buf) -> BatchArrays:
+        (n,) = struct.unpack_from("<I", buf, 0)
+        hdr = pickle.loads(buf[4:4 + n])
+        off = (4 + n + 15) // 16 * 16
+        return BatchArrays.from_wire(hdr, [buf[off:]])
+
     def send_batch(self, batch: BatchArrays, ranks: Optional[List[int]] = None):
+        if self.ring_w is not None:
+            assert ranks is None
+            self.ring_w.send(self._encode_batch(batch), 0)
+            return
         if not self.batch_out:
             return
-        hdr, bufs = batch.to_wire()
-        frames = [pickle.dumps(("batch", hdr), protocol=pickle.HIGHEST_PROTOCOL)] + bufs
+        msg = b"B" + self._encode_batch(batch)
+        copy = len(msg) < (64 << 10)      # small: let zmq copy; large (prefill, pixel payloads): zero-copy
         for r, s in enumerate(self.batch_out, start=1):
             if ranks is None or r in ranks:
-                s.send_multipart(frames, copy=False)
+                s.send(msg, copy=copy)
 
     def broadcast_control(self, cmd: tuple):
-        frames = [pickle.dumps(("control", cmd), protocol=pickle.HIGHEST_PROTOCOL)]
+        body = pickle.dumps(cmd, protocol=pickle.HIGHEST_PROTOCOL)
+        if self.ring_w is not None:
+            self.ring_w.send(body, 1)
+            return
         for s in self.batch_out:
-            s.send_multipart(frames)
+            s.send(b"C" + body)
 
     def recv_batch(self, timeout_ms: int = 0):
         """-> ("batch", BatchArrays) | ("control", cmd) | None"""
+        if self.ring_r is not None:
+            got = self.ring_r.recv()
+            if got is None and timeout_ms > 0:
+                deadline = time.monotonic() + timeout_ms / 1e3
+                while got is None and time.monotonic() < deadline:
+                    time.sleep(0.00005)
+                    got = self.ring_r.recv()
+            if got is None:
+                return None
+            kind, payload = got
+            return ("control", pickle.loads(payload)) if kind == 1 else ("batch", self._decode_batch(memoryview(payload)))
         if self.batch_in is None or not self.batch_in.poll(timeout=timeout_ms):
             return None
-        frames = self.batch_in.recv_multipart(copy=False)
-        kind, payload = pickle.loads(frames[0].buffer)
-        if kind == "batch":
-            return "batch", BatchArrays.from_wire(payload, [f.buffer for f in frames[1:]])
-        return kind, payload
+        buf = self.batch_in.recv(copy=False).buffer
+        if bytes(buf[:1]) == b"C":
+            return "control", pickle.loads(buf[1:])
+        return "batch", self._decode_batch(buf[1:])
 
     # output rank -> driver -----------------------------------------------------------------------
     def send_tokens(self, batch_id: int, tokens: List[int]):
@@ -159,6 +218,11 @@ class Comm:
                 s.close(0)
         self.sock_fe_in = self.sock_fe_out = self.batch_in = self.tok_in = self.tok_out = None
         self.batch_out = []
+        if self.ring_w is not None:
+            self.ring_w.close(unlink=True)
+        if self.ring_r is not None:
+            self.ring_r.close()
+        self.ring_w = self.ring_r = None
         if self.tcp_host is None and self.base.startswith("ipc://"):
             import glob
             root = self.base[len("ipc://"):]

@@ -437,13 +437,17 @@ class _NoFrontend:
         from gllm_b200.engine.comm import make_socket
         P, L = zmq.PUSH, zmq.PULL
         c.ctx = zmq.Context.instance()
+        ring = c.use_shm_ring()
+        if ring:
+            c.init_ring()
         if c.rank == 0:
-            for r in range(1, c.world_size):
+            for r in range(1, c.world_size if not ring else 1):
                 c.batch_out.append(make_socket(c.ctx, P, c._addr("batch", r), bind=False))
             if c.output_rank != 0:
                 c.tok_in = make_socket(c.ctx, L, c._addr("tok"), bind=True)
         else:
-            c.batch_in = make_socket(c.ctx, L, c._addr("batch", c.rank), bind=True)
+            if not ring:
+                c.batch_in = make_socket(c.ctx, L, c._addr("batch", c.rank), bind=True)
             if c.rank == c.output_rank:
                 c.tok_out = make_socket(c.ctx, P, c._addr("tok"), bind=False)
         return self

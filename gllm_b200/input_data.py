@@ -9,11 +9,21 @@ gllm/worker.py:131-136).
 """
 from __future__ import annotations
 
+import math
 from dataclasses import dataclass, field
 from typing import List, Optional
 
 import numpy as np
 import torch
+
+
+class _DtypeCache(dict):
+    def __missing__(self, key):
+        self[key] = np.dtype(key)
+        return self[key]
+
+
+_WIRE_DTYPES = _DtypeCache()
 
 
 @dataclass
@@ -81,11 +91,12 @@ class BatchArrays:
     @staticmethod
     def from_wire(hdr, bufs) -> "BatchArrays":
         kw = {}
-        blob = np.frombuffer(bufs[0], dtype=np.uint8)
+        blob = bufs[0]
         for n, dt, shape, off in hdr["arrays"]:
-            dtype = np.dtype(dt)
-            count = int(np.prod(shape)) if len(shape) else 1
-            kw[n] = np.frombuffer(blob, dtype=dtype, count=count, offset=off).reshape(shape)
+            if len(shape) == 1:     # (hot path on every peer every step: no np.prod / reshape for 1-D arrays)
+                kw[n] = np.frombuffer(blob, dtype=_WIRE_DTYPES[dt], count=shape[0], offset=off)
+            else:
+                kw[n] = np.frombuffer(blob, dtype=_WIRE_DTYPES[dt], count=math.prod(shape), offset=off).reshape(shape)
         s = hdr["scalars"]
         return BatchArrays(**kw, num_decode_seqs=s[0], num_seqs=s[1], num_tokens=s[2], max_q_len=s[3],
                            max_seq_len=s[4], all_greedy=s[5], need_penalty=s[6], batch_id=s[7], mm=hdr.get("mm"))

@@ -429,3 +429,48 @@ def test_util_helpers():
     async def run():
         return await utils.make_async(lambda a, b=0: a + b)(2, b=3)
     assert asyncio.run(run()) == 5
+
+
+def test_shm_ring_broadcast_wrap_and_flow_control():
+    """engine/shm_ring.py: every consumer sees every record in order, records never wrap (skip marker), the
+    producer blocks instead of overwriting unread bytes, late attachers start from the beginning."""
+    import os
+    import uuid
+    from gllm_b200.engine.shm_ring import RingReader, RingWriter
+    name = f"gllm_b200_test_{uuid.uuid4().hex[:10]}"
+    r_early = RingReader(name, 0)
+    assert r_early.recv() is None                          # producer not there yet: lazy attach
+    w = RingWriter(name, 2, capacity=8192)
+    r_late = RingReader(name, 1)
+    try:
+        rng = random.Random(0)
+        sent = []
+        got = {0: [], 1: []}
+        for i in range(400):
+            payload = bytes([i % 251]) * rng.randrange(1, 1500)
+            kind = i % 2
+            while True:
+                try:
+                    w.send(payload, kind, timeout_s=0.0)
+                    break
+                except TimeoutError:                       # ring full: consumers must release first
+                    for k, r in ((0, r_early), (1, r_late)):
+                        m = r.recv()
+                        if m is not None:
+                            got[k].append(m)
+            sent.append((kind, payload))
+            if rng.random() < 0.5:
+                m = r_early.recv()
+                if m is not None:
+                    got[0].append(m)
+        for k, r in ((0, r_early), (1, r_late)):
+            while True:
+                m = r.recv()
+                if m is None:
+                    break
+                got[k].append(m)
+        assert got[0] == sent and got[1] == sent
+        assert w.write > 10 * 8192                         # wrapped many times
+    finally:
+        r_early.close(); r_late.close(); w.close()
+    assert not os.path.exists(f"/dev/shm/{name}")

@@ -91,3 +91,11 @@ def test_vision_tower_tp2_matches_replicated(which):
     with open(out) as f:
         res = json.load(f)
     assert res["ok"], res
+
+
+@pytest.mark.parametrize("pp,tp,port", [(1, 2, 29921), (2, 2, 29931)])
+def test_shared_memory_batch_ring_matches_single(single, monkeypatch, pp, tp, port):
+    """GLLM_BATCH_TRANSPORT=shm: the driver's batches (and control messages) reach the other ranks through the
+    shared-memory broadcast ring instead of ZeroMQ sockets."""
+    monkeypatch.setenv("GLLM_BATCH_TRANSPORT", "shm")
+    assert _run(pp, tp, port=port) == single

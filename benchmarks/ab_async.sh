@@ -11,10 +11,18 @@ run() {
     python bench.py --steps 1 --warmup 1 "$@"
   fi
 }
-for arm in "" "--async-schedule"; do
-  run $arm "$@" 2>&1 | grep "^{" | python -c "
-import json, sys
+report() {
+  grep "^{" | python -c "
+import json, os, sys
 d = json.loads(sys.stdin.read())
-print('async' if d['config'].get('async_schedule') else 'sync ', 'tok/s', d['value'], 'ms/pass', d['ms_per_step'],
-      'gpu_busy', d['config']['gpu_busy_fraction'], 'p50_tpot', d['latency']['p50_tpot_ms'])"
+print(os.environ.get('ARM', ''), 'async' if d['config'].get('async_schedule') else 'sync ', 'tok/s', d['value'],
+      'ms/pass', d['ms_per_step'], 'gpu_busy', d['config']['gpu_busy_fraction'], 'p50_tpot', d['latency']['p50_tpot_ms'])"
+}
+for arm in "" "--async-schedule"; do
+  ARM="zmq" run $arm "$@" 2>&1 | ARM="zmq" report
 done
+if [ "$N" -gt 1 ]; then   # driver -> peer batch fan-out through the shared-memory ring instead of ZeroMQ
+  for arm in "" "--async-schedule"; do
+    GLLM_BATCH_TRANSPORT=shm run $arm "$@" 2>&1 | ARM="shm" report
+  done
+fi

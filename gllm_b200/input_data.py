@@ -271,7 +271,12 @@ class InputData:
         i32, f32 = torch.int32, torch.float32
 
         def buf(shape, dtype):
-            return (torch.zeros(shape, dtype=dtype, pin_memory=pin), torch.zeros(shape, dtype=dtype, device=self.device))
+            # TWO pinned staging buffers per array, alternated every step: with asynchronous scheduling the host
+            # assembles step N+1 while the H2D copies of step N may still be queued behind step N-1's kernels
+            hosts = [torch.zeros(shape, dtype=dtype, pin_memory=pin) for _ in range(2)]
+            return ([(h, h.numpy()) for h in hosts], torch.zeros(shape, dtype=dtype, device=self.device))
+
+        self._flip = 0
 
         self._tokens = buf((max_tokens,), i32)
         self._positions = buf((3, max_tokens) if mrope else (max_tokens,), i32)
@@ -294,17 +299,18 @@ class InputData:
         self.padded_tokens = 0  # > 0 when padded to a CUDA-graph bucket
         self.decode_splits = None  # None: pick per batch (eager); int: fixed (CUDA graphs)
 
-    @staticmethod
-    def _put(pair, arr: np.ndarray, rows=None):
-        host, dev = pair
-        src = torch.from_numpy(np.ascontiguousarray(arr))
+    def _put(self, pair, arr: np.ndarray):
+        """numpy array -> this step's pinned staging buffer (plain numpy store through a shared-memory view: no
+        tensor wrapping per array) -> one non-blocking H2D copy."""
+        stages, dev = pair
+        host, host_np = stages[self._flip]
         if arr.ndim == 1:
             n = arr.shape[0]
-            host[:n].copy_(src)
+            host_np[:n] = arr
             dev[:n].copy_(host[:n], non_blocking=True)
         else:
             r, c = arr.shape
-            host[:r, :c].copy_(src)
+            host_np[:r, :c] = arr
             dev[:r, :c].copy_(host[:r, :c], non_blocking=True)
 
     def load(self, batch: BatchArrays):
@@ -312,6 +318,7 @@ class InputData:
         assert batch.num_seqs <= self.max_seqs, (batch.num_seqs, self.max_seqs)
         assert batch.block_table.shape[1] <= self.max_blocks
         self.batch = batch
+        self._flip ^= 1
         self.num_tokens, self.num_seqs = batch.num_tokens, batch.num_seqs
         self.num_decode_seqs = batch.num_decode_seqs
         self.num_emit = int(batch.logits_idx.shape[0])
@@ -320,7 +327,7 @@ class InputData:
         self._put(self._tokens, batch.tokens)
         if self.mrope:
             pos = batch.positions if batch.positions.ndim == 2 else np.broadcast_to(batch.positions, (3, batch.num_tokens))
-            self._put(self._positions, np.ascontiguousarray(pos))
+            self._put(self._positions, pos)
         else:
             self._put(self._positions, batch.positions if batch.positions.ndim == 1 else batch.positions[0])
         self._put(self._slots, batch.slot_mapping)

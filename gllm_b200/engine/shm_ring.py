@@ -31,6 +31,7 @@ MAGIC = 0x676C6C6D5F623230     # "gllm_b20"
 HDR_BYTES = 4096
 SKIP = 0xFFFFFFFF
 KIND_BATCH, KIND_CONTROL = 0, 1
+MORE = 0x100                   # kind flag: the message continues in the next record
 
 
 def _attach_untracked(name: str) -> shared_memory.SharedMemory:
@@ -81,12 +82,18 @@ class RingWriter:
             time.sleep(0)
 
     def send(self, payload, kind: int = KIND_BATCH, timeout_s: float = 60.0):
+        """Messages larger than a quarter of the ring (pixel payloads of multimodal prefills) travel as a chain of
+        records flagged MORE; the consumers re-assemble them."""
         mv = memoryview(payload).cast("B")
+        limit = self.capacity // 4 - 64
+        while len(mv) > limit:
+            self._send_one(mv[:limit], kind | MORE, timeout_s)
+            mv = mv[limit:]
+        self._send_one(mv, kind, timeout_s)
+
+    def _send_one(self, mv, kind: int, timeout_s: float):
         n = len(mv)
         rec = 8 + (n + 15) // 16 * 16
-        if rec > self.capacity // 2:
-            raise ValueError(f"message of {n} bytes does not fit the {self.capacity >> 20} MiB batch ring "
-                             f"(raise GLLM_SHM_RING_MB or use GLLM_BATCH_TRANSPORT=zmq)")
         off = self.write % self.capacity
         if off + rec > self.capacity:              # does not fit before the end: skip marker, start over
             pad = self.capacity - off
@@ -118,6 +125,7 @@ class RingReader:
         self.name, self.index = name, index
         self.shm: Optional[shared_memory.SharedMemory] = None
         self.read = 0
+        self.parts = []                # records of a chained message received so far
 
     def _attach(self) -> bool:
         try:
@@ -149,6 +157,12 @@ class RingReader:
             payload = self.data[off + 8:off + 8 + n].tobytes()     # copy out: the slot is recycled after release
             self.read += 8 + (n + 15) // 16 * 16
             self.u64[16 + 8 * self.index] = self.read              # release
+            if kind & MORE:                                        # chained message: keep collecting
+                self.parts.append(payload)
+                continue
+            if self.parts:
+                payload = b"".join(self.parts) + payload
+                self.parts = []
             return kind, payload
 
     def close(self):

@@ -440,15 +440,20 @@ def test_shm_ring_broadcast_wrap_and_flow_control():
     name = f"gllm_b200_test_{uuid.uuid4().hex[:10]}"
     r_early = RingReader(name, 0)
     assert r_early.recv() is None                          # producer not there yet: lazy attach
-    w = RingWriter(name, 2, capacity=8192)
+    w = RingWriter(name, 2, capacity=32768)
     r_late = RingReader(name, 1)
     try:
         rng = random.Random(0)
         sent = []
         got = {0: [], 1: []}
-        for i in range(400):
-            payload = bytes([i % 251]) * rng.randrange(1, 1500)
+        for i in range(600):
+            big = i % 50 == 49
+            payload = bytes([i % 251]) * (9000 if big else rng.randrange(1, 1500))    # 9000 > ring / 4: chained records
             kind = i % 2
+            if big:       # a chained send must not time out half way (single-threaded test): make room first
+                for k, r in ((0, r_early), (1, r_late)):
+                    while (m := r.recv()) is not None:
+                        got[k].append(m)
             while True:
                 try:
                     w.send(payload, kind, timeout_s=0.0)
@@ -470,7 +475,7 @@ def test_shm_ring_broadcast_wrap_and_flow_control():
                     break
                 got[k].append(m)
         assert got[0] == sent and got[1] == sent
-        assert w.write > 10 * 8192                         # wrapped many times
+        assert w.write > 5 * 32768                         # wrapped several times
     finally:
         r_early.close(); r_late.close(); w.close()
     assert not os.path.exists(f"/dev/shm/{name}")

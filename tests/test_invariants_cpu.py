@@ -195,3 +195,80 @@ def test_lookahead_scheduling_equals_synchronous(seed, n_req, pages, method, max
         else:   # an aborted request may have streamed a prefix of its tokens, never anything else
             got = prod_a.get(a.seq_id, [])
             assert got == want[:len(got)]
+
+
+@settings(max_examples=200, deadline=None, derandomize=True)
+@given(ops=st.lists(st.tuples(st.sampled_from(["alloc", "alloc_id", "free"]), st.integers(0, 15)), max_size=120))
+def test_id_allocator_matches_a_simple_model(ops):
+    """The O(1) linked-list allocator behaves like the obvious model: allocate from the head of the free order,
+    freed ids go to the tail, specific ids can be taken from anywhere."""
+    from gllm_b200.id_allocator import IDAllocator
+    a = IDAllocator(0, 15)
+    order = list(range(16))            # model of the free list, head first
+    for op, x in ops:
+        if op == "alloc":
+            if order:
+                assert a.allocate() == order.pop(0)
+            else:
+                with pytest.raises(RuntimeError):
+                    a.allocate()
+        elif op == "alloc_id":
+            assert a.allocate(x) == x
+            if x in order:
+                order.remove(x)
+        else:
+            if x in order:
+                with pytest.raises(RuntimeError):
+                    a.free(x)
+            else:
+                a.free(x)
+                order.append(x)
+        assert a.get_num_free_ids() == len(order)
+        assert all(a.is_free(i) == (i in order) for i in range(16))
+
+
+@settings(max_examples=300, deadline=None, derandomize=True)
+@given(layers=st.integers(1, 130), pp=st.integers(1, 16))
+def test_layer_partition_covers_every_layer_once(layers, pp):
+    from gllm_b200.parallel.state import partition_layers
+    if pp > layers:
+        return
+    parts = partition_layers(layers, pp)
+    assert len(parts) == pp and all(len(r) > 0 for r in parts)
+    flat = [i for r in parts for i in r]
+    assert flat == list(range(layers))                       # contiguous, ordered, complete
+    assert max(len(r) for r in parts) - min(len(r) for r in parts) <= max(1, (layers + pp - 1) // pp - 1)
+
+
+@settings(max_examples=80, deadline=None, derandomize=True)
+@given(seed=st.integers(0, 10 ** 6), b=st.integers(1, 6), v=st.integers(2, 300), k=st.integers(-1, 40),
+       p=st.floats(0.05, 1.0), temp=st.floats(0.1, 2.0))
+def test_reference_sampler_draws_inside_the_filtered_support(seed, b, v, k, p, temp):
+    """ops/ref.py is the oracle of the sm_100a sampler kernel: a drawn token must survive the top-k and nucleus
+    filters, greedy rows (top_k == 1) must be the argmax, the filtered distribution is normalised."""
+    import torch
+    from gllm_b200.ops import ref
+    g = torch.Generator().manual_seed(seed)
+    logits = torch.randn(b, v, generator=g) * 3
+    tk = torch.full((b,), k, dtype=torch.int32)
+    tk[0] = 1                                                   # one greedy row in every batch
+    tp = torch.full((b,), p)
+    t = torch.full((b,), temp)
+    probs = ref.sample_filter(logits, t, tk, tp)
+    assert torch.allclose(probs.sum(-1), torch.ones(b), atol=1e-5)
+    kk = tk.clone().long()
+    kk[(kk <= 0) | (kk > v)] = v
+    assert ((probs > 0).sum(-1) <= kk).all() or bool((logits.sort(-1).values.diff(dim=-1) == 0).any())  # ties may widen top-k
+    for s in range(3):
+        tok = ref.sample(logits, t, tk, tp, generator=torch.Generator().manual_seed(seed + s)).long()
+        assert (probs.gather(1, tok.view(-1, 1)) > 0).all()
+        assert int(tok[0]) == int(logits[0].argmax())
+    # nucleus: the kept set is the smallest prefix (by probability) whose mass reaches top_p
+    base = ref.sample_filter(logits, t, tk, None)
+    for r in range(b):
+        kept = probs[r] > 0
+        mass_kept = float(base[r][kept].sum())
+        assert mass_kept >= min(p, 1.0) - 1e-4
+        if kept.sum() > 1:
+            smallest = float(base[r][kept].min())
+            assert mass_kept - smallest < p + 1e-4              # dropping the weakest kept token would fall short

@@ -323,3 +323,55 @@ def test_deepseek_fp8_checkpoint_keeps_experts_quantised():
     same_first = sum(s.token_ids[len(p)] == _hf_greedy(m, p, 1)[0] for p, s in zip(PROMPTS, outs))
     assert same_first >= len(PROMPTS) - 1
     llm.shutdown()
+
+
+@pytest.mark.parametrize("async_schedule", [False, True])
+def test_random_arrivals_and_aborts_through_the_engine(async_schedule):
+    """Front-end + worker + scheduler + runner under churn: requests arrive at random ticks, some are aborted at
+    random ticks (possibly before they were ever scheduled, mid-prefill, mid-decode). The engine must drain, give
+    every page back, free every sequence id, and the surviving requests must get exactly the tokens of a quiet run."""
+    import random
+    from gllm_b200 import LLM
+    from gllm_b200.models.presets import tiny
+    cfg = tiny("Qwen3ForCausalLM", num_hidden_layers=1, max_position_embeddings=512)
+
+    def engine():
+        return LLM(cfg, load_format="dummy", maxp=24, maxd=6, num_cpu_pages=96, page_size=4, log_stats=False,
+                   device="cpu", kvthresh=0.0, async_schedule=async_schedule, enable_prefix_caching=True, seed=0)
+
+    for seed in range(int(os.environ.get("GLLM_CHURN_SEEDS", "4"))):
+        rng = random.Random(seed)
+        prompts = [[rng.randrange(5, 300) for _ in range(rng.randrange(1, 30))] for _ in range(14)]
+        outs = [rng.randrange(1, 14) for _ in prompts]
+        llm = engine()
+        quiet = [s.token_ids for s in llm.generate(tokens=prompts, output_lens=outs, ignore_eos=True)]
+        llm.shutdown()
+
+        llm = engine()
+        seqs = [llm.allocate_seq(p, o, True, top_k=1) for p, o in zip(prompts, outs)]
+        arrive = sorted((rng.randrange(0, 25), i) for i in range(len(seqs)))
+        aborts = {i: rng.randrange(0, 40) for i in rng.sample(range(len(seqs)), 5)}
+        aborted = set()
+        tick = 0
+        while len(llm.finished) < len(seqs):
+            while arrive and arrive[0][0] <= tick:
+                llm.add_requests([seqs[arrive.pop(0)[1]]])
+            for i, t in aborts.items():
+                if t == tick and seqs[i].seq_id in llm.running_maps:
+                    llm.abort([seqs[i].seq_id])
+                    aborted.add(i)
+            llm.schedule()
+            tick += 1
+            if tick > 40 and not arrive and not llm.running_maps and not llm.wait_lists:
+                break
+            assert tick < 20000, "engine did not drain"
+        for i, s in enumerate(seqs):
+            if i in aborted:
+                assert s.token_ids == quiet[i][:len(s.token_ids)]      # a prefix of the quiet stream at most
+            else:
+                assert s.token_ids == quiet[i], (seed, i)
+        mm = llm.worker.mm
+        assert mm.get_num_free_pages() == mm.num_pages - 1, "pages leaked"          # all but the dummy page
+        assert not llm.running_maps
+        assert llm.id_allocator.get_num_free_ids() == 100000 - 0                  # every sequence id returned
+        llm.shutdown()

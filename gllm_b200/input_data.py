@@ -118,8 +118,9 @@ def _build_decode_fast(entries, page_size: int, batch_id: int, prev: "BatchArray
     derived from the previous arrays with vectorised numpy (new arrays, never in place: zero-copy zmq sends may
     still reference the old ones); only rows that crossed a page boundary touch their Python page table."""
     b = len(entries)
-    if prev is None or prev.seq_ids is None or b != prev.num_seqs or prev.num_decode_seqs != b or prev.need_penalty \
-            or prev.mm is not None or prev.positions.ndim != 1:
+    # (a SUBSET of the previous rows is fine too: sequences finish all the time and the survivors keep decoding)
+    if prev is None or prev.seq_ids is None or b > prev.num_seqs or prev.num_decode_seqs != prev.num_seqs \
+            or prev.need_penalty or prev.mm is not None or prev.positions.ndim != 1:
         return None
     # the scheduler re-queues finished-step sequences head-first, so the row order flips between iterations:
     # map every entry to its row in the previous batch
@@ -154,7 +155,7 @@ def _build_decode_fast(entries, page_size: int, batch_id: int, prev: "BatchArray
     feed = perm.astype(np.int32) if (tokens < 0).any() else None   # lookahead rows: token still on the device
     return BatchArrays(feed_src=feed,
         tokens=tokens, positions=starts, slot_mapping=slots.astype(np.int32), block_table=bt, seq_lens=seq_lens,
-        query_start_loc=prev.query_start_loc, logits_idx=prev.logits_idx, emit_seq=prev.emit_seq,
+        query_start_loc=prev.query_start_loc[:b + 1], logits_idx=prev.logits_idx[:b], emit_seq=prev.emit_seq[:b],
         temperature=prev.temperature[perm], top_k=prev.top_k[perm], top_p=prev.top_p[perm],
         rep_penalty=prev.rep_penalty[perm], state_slot=prev.state_slot[perm], num_decode_seqs=b, num_seqs=b, num_tokens=b, max_q_len=1,
         max_seq_len=int(seq_lens.max()), all_greedy=prev.all_greedy, need_penalty=False, batch_id=batch_id,

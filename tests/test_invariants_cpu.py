@@ -90,7 +90,7 @@ def test_random_streams_keep_kv_bookkeeping_consistent(seed, n_req, pages, metho
             inc = build_batch(batch, PAGE, 64, bid, prev=prev_arrays if pp == 1 else None)
             full = build_batch(batch, PAGE, 64, bid, prev=None)
             for name in ("tokens", "positions", "slot_mapping", "seq_lens", "query_start_loc", "logits_idx",
-                         "temperature", "top_k", "top_p", "rep_penalty"):
+                         "temperature", "top_k", "top_p", "rep_penalty", "emit_seq", "state_slot"):
                 assert np.array_equal(getattr(inc, name), getattr(full, name)), name
             w = full.block_table.shape[1]
             for r in range(len(batch)):   # compare the pages each row really uses

@@ -49,7 +49,10 @@ E2E_BUCKETS = (0.1, 0.25, 0.5, 1.0, 2.5, 5.0, 10.0, 20.0, 40.0, 60.0, 120.0, 300
 
 
 class AsyncStream:
-    def __init__(self, raw_request=None):
+    def __init__(self, raw_request=None, stop=None):
+        self.stop = [x for x in ([stop] if isinstance(stop, str) else list(stop or [])) if x]
+        self._held = ""
+        self.stop_hit = False
         self._queue: asyncio.Queue = asyncio.Queue()
         self._finished = False
         self._raw_request = raw_request
@@ -61,11 +64,38 @@ class AsyncStream:
         self.seq_id = -1
 
     def put(self, item: str):
-        if not self._finished:
+        """Queue a text delta. With stop strings (OpenAI `stop`; not honoured by the reference) the text that could
+        still turn into a stop string is held back; on a hit the text before it is delivered, the stream ends with
+        finish_reason "stop" and `stop_hit` tells the engine to abort the request."""
+        if self._finished:
+            return
+        if not self.stop:
             self._queue.put_nowait(item)
+            return
+        buf = self._held + item
+        cut = min((i for i in (buf.find(s) for s in self.stop) if i >= 0), default=-1)
+        if cut >= 0:
+            self._held = ""
+            if cut:
+                self._queue.put_nowait(buf[:cut])
+            self.stop_hit = True
+            self.finish("stop")
+            return
+        hold = 0      # longest suffix of buf that is a proper prefix of some stop string
+        for s in self.stop:
+            for k in range(min(len(s) - 1, len(buf)), hold, -1):
+                if buf.endswith(s[:k]):
+                    hold = k
+                    break
+        if len(buf) > hold:
+            self._queue.put_nowait(buf[:len(buf) - hold])
+        self._held = buf[len(buf) - hold:] if hold else ""
 
     def finish(self, reason: str = "stop"):
         if not self._finished:
+            if self._held:                     # generation ended while a possible stop prefix was held back
+                self._queue.put_nowait(self._held)
+                self._held = ""
             self.finish_reason = reason
             self._queue.put_nowait(StopAsyncIteration())
             self._finished = True
@@ -105,10 +135,10 @@ class AsyncLLM(LLM):
 
     async def add_requests_async(self, raw_request, token_ids: List[int], output_len=None, ignore_eos=False,
                                  temperature=None, top_p=None, top_k=None, repetition_penalty=None,
-                                 mm_contents=None) -> AsyncStream:
+                                 mm_contents=None, stop=None) -> AsyncStream:
         seq = self.allocate_seq(token_ids, output_len, ignore_eos, temperature, top_p, top_k, repetition_penalty,
                                 mm_contents)
-        stream = AsyncStream(raw_request)
+        stream = AsyncStream(raw_request, stop)
         stream.prompt_tokens = len(token_ids)
         stream.seq_id = seq.seq_id
         self.async_streams[seq.seq_id] = stream
@@ -170,6 +200,9 @@ class AsyncLLM(LLM):
             else:
                 st.put(" ".join(str(t) for t in seq.token_ids[seq.cur_length:seq.known_len]) + " ")
                 seq.cur_length = seq.known_len
+            if st.stop_hit and not seq.is_abort:      # a stop string completed: stop generating for this request
+                self.abort([seq.seq_id])
+                seq.is_abort = True
         self._pending_tokens = []
         for seq in self.finished:
             st = self.async_streams.pop(seq.seq_id, None)

@@ -123,8 +123,6 @@ def build_app(engine):
     global llm
     llm = engine
     app = fastapi.FastAPI(title="gllm_b200")
-    loop_exec = asyncio.get_event_loop().run_in_executor if False else None  # noqa: F841
-
     async def _in_thread(fn, *a, **kw):
         return await asyncio.get_running_loop().run_in_executor(None, lambda: fn(*a, **kw))
 
@@ -181,7 +179,7 @@ def build_app(engine):
             return _error("seq length exceeds max model length")
         stream = await llm.add_requests_async(raw_request, token_ids, request.output_len(), request.ignore_eos,
                                               request.temperature, request.top_p, request.top_k,
-                                              request.repetition_penalty, mm_contents)
+                                              request.repetition_penalty, mm_contents, stop=request.stop)
         if request.stream:
             return StreamingResponse(chat_completion_stream_generator(stream, request),
                                      media_type="text/event-stream")
@@ -197,7 +195,7 @@ def build_app(engine):
             return _error("seq length exceeds max model length")
         stream = await llm.add_requests_async(raw_request, token_ids, request.max_tokens, request.ignore_eos,
                                               request.temperature, request.top_p, request.top_k,
-                                              request.repetition_penalty)
+                                              request.repetition_penalty, stop=request.stop)
         if request.stream:
             return StreamingResponse(completion_stream_generator(stream, request), media_type="text/event-stream")
         return JSONResponse(content=(await completion_generator(stream, request)).model_dump())

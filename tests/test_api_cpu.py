@@ -124,3 +124,41 @@ def test_engine_metrics_after_requests(client):
     assert engine.last_stats["prefill_step_tokens"] > 0 and engine.last_stats["decode_step_seconds"] > 0
     h = engine.hist["ttft"]
     assert h.count == sum(h.counts) >= 4 and engine.hist["tpot"].count > 0
+
+
+def test_stop_strings(client):
+    """OpenAI `stop`: generation ends at the first stop string, which is not part of the returned text; text that
+    might still become a stop string is held back while streaming (the reference ignores `stop`)."""
+    from gllm_b200.engine.async_llm_engine import AsyncStream
+    import asyncio
+
+    async def drain(parts, stop):
+        st = AsyncStream(None, stop)
+        for p in parts:
+            st.put(p)
+        st.finish("length")
+        return "".join([x async for x in st]), st.finish_reason, st.stop_hit
+
+    assert asyncio.run(drain(["ab", "c<", "/s", ">zz"], ["</s>"])) == ("abc", "stop", True)      # split across deltas
+    assert asyncio.run(drain(["ab", "c<", "/x", "y"], ["</s>"])) == ("abc</xy", "length", False)   # false alarm: flushed
+    assert asyncio.run(drain(["abc<"], ["</s>", "q"])) == ("abc<", "length", False)               # held tail released
+    assert asyncio.run(drain(["hello world"], "o w")) == ("hell", "stop", True)
+
+    c, engine = client
+    body = {"prompt": "hello world how are you", "max_tokens": 12, "temperature": 0.0, "top_k": 1, "ignore_eos": True}
+    full = c.post("/v1/completions", json=body).json()["choices"][0]["text"]
+    words = full.split()
+    assert len(words) >= 6
+    stop = " " + words[3] + " "
+    r = c.post("/v1/completions", json=dict(body, stop=[stop])).json()
+    assert r["choices"][0]["finish_reason"] == "stop"
+    assert r["choices"][0]["text"] == full[:full.find(stop)] and stop not in r["choices"][0]["text"]
+    assert r["usage"]["completion_tokens"] < 12                       # the request was cut short in the engine too
+    # streaming: same text, [DONE] framing intact
+    chunks = []
+    with c.stream("POST", "/v1/completions", json=dict(body, stop=stop, stream=True)) as resp:
+        for line in resp.iter_lines():
+            if line.startswith("data: ") and line != "data: [DONE]":
+                chunks.append(json.loads(line[6:]))
+    assert "".join(ch["choices"][0]["text"] for ch in chunks) == full[:full.find(stop)]
+    assert chunks[-1]["choices"][0]["finish_reason"] == "stop"

@@ -114,11 +114,13 @@ class Scheduler:
     # -- inputs -----------------------------------------------------------------------------------
     def add_new_requests(self, seqs: List[Sequence]):
         cap = (self.mm.num_pages - (1 if getattr(self.mm, "dummy_page", None) is not None else 0)) * self.page_size
+        # prefill may only use the pages above the kvthresh reserve (kv_headroom_tokens), decode may use all of them
+        prompt_cap = cap - self.num_kvthresh_pages * self.page_size
         for seq in seqs:
-            if len(seq) + 1 > cap:
+            if len(seq) + 1 > prompt_cap:
                 # the prompt alone can never be resident: it would wait in the queue forever
-                logger.error("request %d: prompt of %d tokens but the KV cache holds %d: rejected", seq.seq_id,
-                             len(seq), cap)
+                logger.error("request %d: prompt of %d tokens but the KV cache can hold %d during prefill: rejected",
+                             seq.seq_id, len(seq), prompt_cap)
                 self.abort_ids.add(seq.seq_id)
             elif len(seq) + seq.output_len > cap:
                 # alone in the pool it would still outgrow it and be preempted/recomputed forever: cap the length

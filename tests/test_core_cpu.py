@@ -325,6 +325,21 @@ def test_oversized_requests_do_not_hang_the_scheduler():
     assert out is not None and out.free_ids == [1] and big not in sch.seqs_to_prefill
     ents = sch.schedule_once()
     assert ents and ents[0].seq is greedy
+    # the prefill budget excludes the kvthresh reserve: a prompt that only fits into the reserve is rejected too
+    mm = MemoryManager(20, 16)                                  # 20 pages, reserve = int(0.25 * 20) = 5 pages
+    sch = Scheduler(mm, maxp=64, maxd=8, page_size=16, kvthresh=0.25, log=False)
+    fits, too_big = Sequence(3, list(range(15 * 16 - 1)), [1], 4, True), Sequence(4, list(range(15 * 16)), [1], 4, True)
+    sch.add_new_requests([too_big, fits])
+    out = sch.check_abort_seqs()
+    assert out is not None and out.free_ids == [4]
+    for _ in range(40):                                         # the admitted one really gets through its prefill
+        ents = sch.schedule_once()
+        assert ents, "admitted prompt stalled"
+        sch.add_next_tokens([5] * sum(e.emits for e in ents))
+        sch.process_output()
+        if fits.computed_token_num >= fits.prompt_len:
+            break
+    assert fits.computed_token_num >= fits.prompt_len
 
 
 @pytest.mark.parametrize("tp", [1, 2, 4, 8])

@@ -45,12 +45,13 @@ def check_invariants(mm: PrefixMemoryManager, live):
 @settings(max_examples=int(__import__("os").environ.get("GLLM_HYP_EXAMPLES", "60")), deadline=None, derandomize=not __import__("os").environ.get("GLLM_HYP_RANDOM"), suppress_health_check=[HealthCheck.too_slow])
 @given(seed=st.integers(0, 10 ** 6), n_req=st.integers(1, 14), pages=st.integers(10, 40),
        method=st.sampled_from(["chunked_prefill", "token_throttling", "split_pd"]),
-       maxp=st.sampled_from([8, 16, 64]), abort_rate=st.sampled_from([0.0, 0.1]), pp=st.sampled_from([1, 2]))
-def test_random_streams_keep_kv_bookkeeping_consistent(seed, n_req, pages, method, maxp, abort_rate, pp):
+       maxp=st.sampled_from([8, 16, 64]), abort_rate=st.sampled_from([0.0, 0.1]), pp=st.sampled_from([1, 2]),
+       kvthresh=st.sampled_from([0.0, 0.1, 0.3]))
+def test_random_streams_keep_kv_bookkeeping_consistent(seed, n_req, pages, method, maxp, abort_rate, pp, kvthresh):
     rng = random.Random(seed)
     mm = PrefixMemoryManager(pages, PAGE)
     sch = Scheduler(mm, pp_size=pp, world_size=pp, schedule_method=method, maxd=6, maxp=maxp, minp=4, iterp=2,
-                    kvthresh=0.0, page_size=PAGE, log=False)
+                    kvthresh=kvthresh, page_size=PAGE, log=False)
     # prompts drawn from a few shared prefixes so that the prefix cache really gets hits and shared pages
     stems = [[rng.randrange(50) for _ in range(rng.randrange(2, 14))] for _ in range(3)]
     reqs = []
@@ -58,7 +59,7 @@ def test_random_streams_keep_kv_bookkeeping_consistent(seed, n_req, pages, metho
         stem = rng.choice(stems)
         toks = stem[:rng.randrange(1, len(stem) + 1)] + [rng.randrange(50) for _ in range(rng.randrange(0, 6))]
         out = rng.randrange(1, 9)
-        if (len(toks) + out + PAGE - 1) // PAGE > pages - 1:
+        if (len(toks) + out + PAGE - 1) // PAGE > pages - 1 - int(kvthresh * pages):
             continue
         reqs.append(Sequence(i, toks, [2], output_len=out, ignore_eos=True))
     pending = list(reqs)

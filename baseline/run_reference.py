@@ -35,8 +35,10 @@ def qwen3_8b_dir(path):
         json.dump({"eos_token_id": [151645, 151643], "temperature": 0.6, "top_p": 0.95, "top_k": 20}, f)
     tok = Tokenizer(models.WordLevel({f"t{i}": i for i in range(vocab)}, unk_token="t0"))
     tok.pre_tokenizer = pre_tokenizers.Whitespace()
-    PreTrainedTokenizerFast(tokenizer_object=tok, unk_token="t0", eos_token="t151645",
-                            pad_token="t151643").save_pretrained(path)
+    # model_max_length as in the real checkpoint's tokenizer_config.json: the reference derives its admission
+    # limit from it (model_runner.py:135-143) and would otherwise fall back to generation_config.max_length
+    PreTrainedTokenizerFast(tokenizer_object=tok, unk_token="t0", eos_token="t151645", pad_token="t151643",
+                            model_max_length=40960).save_pretrained(path)
     return path
 
 
@@ -63,8 +65,8 @@ def main():
 
     def one_pass():
         t0 = time.perf_counter()
-        seqs = llm.generate(tokens=[list(p) for p in prompts], output_lens=list(outs), temperature=0.0, top_p=1.0,
-                            top_k=1)
+        # sampling arguments left at the reference's defaults: top_k defaults to 1, i.e. greedy (llm_engine.py:316-325)
+        seqs = llm.generate(tokens=[list(p) for p in prompts], output_lens=list(outs))
         dt = time.perf_counter() - t0
         n_out = sum(len(s.token_ids) - s.prompt_len for s in seqs)
         return dt, n_out

@@ -18,6 +18,29 @@ if not logger.handlers:
     logger.setLevel(os.environ.get("GLLM_REF_LOG", "INFO"))
     logger.propagate = False
 
+if not hasattr(logger, "warning_once"):          # vLLM-style helper the reference's utils call on some platforms
+    _seen = set()
+
+    def _warning_once(msg, *args):
+        if msg not in _seen:
+            _seen.add(msg)
+            logger.warning(msg, *args)
+
+    logger.warning_once = _warning_once
+
+if os.environ.get("GLLM_REF_ALIAS_VLLM") == "1":
+    # The reference's native modules (gllm._C, gllm._moe_C, gllm.vllm_flash_attn) ARE vLLM's: its setup.py copies
+    # them out of a vLLM wheel. Here they are taken from the vLLM installed in the image; aliasing the module
+    # names makes sure every shared object is loaded exactly once per process (a second copy of the same library
+    # would register its torch ops twice), whether or not the symlinks under baseline/_ref survived a file copy.
+    import importlib
+    for _ours, _theirs in (("gllm._C", "vllm._C"), ("gllm._moe_C", "vllm._moe_C"),
+                           ("gllm.vllm_flash_attn", "vllm.vllm_flash_attn")):
+        try:
+            sys.modules.setdefault(_ours, importlib.import_module(_theirs))
+        except Exception as _e:  # noqa: BLE001
+            logger.warning("could not alias %s -> %s: %r", _ours, _theirs, _e)
+
 _libs = [p for p in os.environ.get("GLLM_REF_PRELOAD_LIBS", "").split(":") if p]
 if _libs:
     import torch

@@ -70,10 +70,12 @@ def reference_arm(args):
     env["PYTHONPATH"] = os.pathsep.join([ref_root, os.path.join(root, "baseline", "shims"),
                                          env.get("PYTHONPATH", "")])
     try:
-        import vllm
-        stable = os.path.join(os.path.dirname(vllm.__file__), "_C_stable_libtorch.abi3.so")
+        import importlib.util
+        vdir = os.path.dirname(importlib.util.find_spec("vllm").origin)
+        stable = os.path.join(vdir, "_C_stable_libtorch.abi3.so")
         if os.path.exists(stable):
             env["GLLM_REF_PRELOAD_LIBS"] = stable
+        env["GLLM_REF_ALIAS_VLLM"] = "1"
     except Exception:  # noqa: BLE001
         pass
     cmd = [sys.executable, os.path.join(root, "baseline", "run_reference.py"), "--gpus", str(args.gpus),

@@ -1,7 +1,6 @@
 """Synthetic workloads shaped like the reference's datasets (no network: BASELINE.json asks for
 "synthetic ShareGPT-shaped requests"). Optionally reads a local ShareGPT json with --dataset."""
 import json
-import os
 from typing import List, Optional, Tuple
 
 import numpy as np

@@ -2,7 +2,7 @@
 constructor (gllm/llm_engine.py:19-49, gllm/entrypoints/api_server.py:134-278)."""
 from __future__ import annotations
 
-from dataclasses import dataclass, field
+from dataclasses import dataclass
 from typing import List, Optional
 
 

@@ -21,7 +21,6 @@ import uuid
 from dataclasses import dataclass, field
 from typing import List, Optional
 
-import numpy as np
 import zmq
 
 from gllm_b200.input_data import BatchArrays

@@ -13,7 +13,6 @@ temperature=, top_p=, top_k=)`, `chat()`, `add_requests()`, `schedule()`,
 """
 from __future__ import annotations
 
-import itertools
 import os
 import sys
 import time

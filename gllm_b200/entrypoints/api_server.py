@@ -12,7 +12,6 @@ from __future__ import annotations
 
 import argparse
 import asyncio
-import time
 from http import HTTPStatus
 from typing import List, Optional
 

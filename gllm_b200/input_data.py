@@ -10,8 +10,8 @@ gllm/worker.py:131-136).
 from __future__ import annotations
 
 import math
-from dataclasses import dataclass, field
-from typing import List, Optional
+from dataclasses import dataclass
+from typing import Optional
 
 import numpy as np
 import torch

@@ -7,7 +7,6 @@ hand-written kernels in `gllm_b200.ops.sm100`.
 """
 from __future__ import annotations
 
-import math
 from typing import Optional
 
 import torch

@@ -8,7 +8,6 @@ case (T*k + E_local*127 rows), so the block is CUDA-graph capturable.
 """
 from __future__ import annotations
 
-import ctypes
 from typing import Optional
 
 import torch

@@ -250,3 +250,21 @@ def test_mmlu_pro_script_and_chat_clients_against_server():
             srv.wait(timeout=10)
         except Exception:  # noqa: BLE001
             srv.kill()
+
+
+def test_bench_reference_arm_contract_without_gpu():
+    """`bench.py --impl reference` must always exit 0 with ONE JSON line: either the reference's numbers or
+    {"impl": "reference", "unavailable": <why>} (here: no GPU, so the reference's CUDA extensions cannot load)."""
+    env = dict(os.environ, PYTHONPATH=ROOT)
+    env.pop("RANK", None)
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1",
+                        "--warmup", "0"], capture_output=True, text=True, timeout=600, env=env, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and ("unavailable" in d or "value" in d)
+    # ranks other than 0 (torchrun launches N of them) stay silent: the reference spawns its own workers
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2"],
+                       capture_output=True, text=True, timeout=120, env=dict(env, RANK="1", WORLD_SIZE="2"), cwd=ROOT)
+    assert r.returncode == 0 and not r.stdout.strip()

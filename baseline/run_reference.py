@@ -91,8 +91,25 @@ def main():
                    "maxp": args.maxp, "maxd": args.maxd, "native_kernels": "vLLM 0.22 libraries of this image "
                    "(the reference pins vLLM 0.11)"},
         "e2e": {"value": round(value, 2), "unit": "tokens/s"}}), flush=True)
-    os._exit(0)      # the reference's daemon workers die with the front-end
+
+
+def _leave():
+    """The reference's worker processes hold our stdout / stderr pipes: bench.py would wait for EOF until they are
+    gone (also after a failure, if a worker hangs in a collective). bench.py starts this script as the leader of its
+    own process group, so take the whole group down."""
+    sys.stdout.flush()
+    sys.stderr.flush()
+    if os.getpgid(0) == os.getpid():
+        import signal
+        os.killpg(os.getpid(), signal.SIGKILL)
+    os._exit(0)
 
 
 if __name__ == "__main__":
-    main()
+    try:
+        main()
+    except BaseException:  # noqa: BLE001
+        import traceback
+        traceback.print_exc()
+    finally:
+        _leave()

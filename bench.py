@@ -82,7 +82,7 @@ def reference_arm(args):
            "--steps", str(args.steps), "--warmup", str(args.warmup), "--num-prompts", str(args.num_prompts),
            "--maxp", str(args.maxp), "--maxd", str(args.maxd), "--max-cuda-graph-bs", str(args.max_cuda_graph_bs),
            "--seed", str(args.seed)]
-    limit = int(os.environ.get("GLLM_REF_TIMEOUT", "1500"))
+    limit = int(os.environ.get("GLLM_REF_TIMEOUT", "1200"))
     try:
         # own process group: on a timeout the reference's spawned workers are taken down with the front-end
         proc = subprocess.Popen(cmd, env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True,

@@ -15,6 +15,7 @@ from __future__ import annotations
 
 import os
 import sys
+import threading
 import time
 from typing import Dict, List, Optional
 
@@ -85,6 +86,7 @@ class LLM:
         self.wait_lists: List[Sequence] = []
         self.abort_ids: List[int] = []
         self.control_cmds: List[tuple] = []
+        self._inbox_lock = threading.Lock()
         self.finished: List[Sequence] = []
         self.last_stats: dict = {}
         self.worker: Optional[Worker] = None
@@ -201,7 +203,9 @@ class LLM:
                      top_k=None, repetition_penalty=None, mm_contents=None) -> Sequence:
         """Defaults: temperature/top_p/repetition_penalty from generation_config, top_k = 1
         (greedy) unless given (reference: gllm/llm_engine.py:305-337)."""
-        seq = Sequence(self.id_allocator.allocate(), token_ids, self.finish_tokens, output_len, ignore_eos,
+        with self._inbox_lock:      # ids are freed by the tick thread (`_apply`)
+            sid = self.id_allocator.allocate()
+        seq = Sequence(sid, token_ids, self.finish_tokens, output_len, ignore_eos,
                        self.default_temperature if temperature is None else temperature,
                        self.default_top_p if top_p is None else top_p,
                        1 if top_k is None else top_k,
@@ -215,11 +219,16 @@ class LLM:
         seq.arrival_time = time.time()
         return seq
 
+    # The three inboxes below are filled from request handlers (event-loop thread of the API server) while the
+    # engine tick runs in a worker thread: every append and the swap in `_send` hold `_inbox_lock`, so a request
+    # can never land in a list the tick has already shipped (the reference has this race).
     def add_requests(self, seqs: List[Sequence]):
-        self.wait_lists.extend(seqs)
+        with self._inbox_lock:
+            self.wait_lists.extend(seqs)
 
     def abort(self, seq_ids: List[int]):
-        self.abort_ids.extend(seq_ids)
+        with self._inbox_lock:
+            self.abort_ids.extend(seq_ids)
 
     # -------------------------------------------------------------------------------------------
     # engine tick
@@ -227,17 +236,19 @@ class LLM:
     def _send(self):
         if not (self.wait_lists or self.abort_ids or self.control_cmds):
             return
-        for seq in self.wait_lists:
+        with self._inbox_lock:
+            wait, self.wait_lists = self.wait_lists, []
+            aborts, self.abort_ids = self.abort_ids, []
+            cmds, self.control_cmds = self.control_cmds, []
+        for seq in wait:
             self.running_maps[seq.seq_id] = seq
-        if self.control_cmds:
-            for cmd in self.control_cmds[:-1]:
+        if cmds:
+            for cmd in cmds[:-1]:
                 self._post(IPCPackage(control_cmd=cmd))
-            pkg = IPCPackage(schedule_lists=self.wait_lists, abort_ids=self.abort_ids,
-                             control_cmd=self.control_cmds[-1])
+            pkg = IPCPackage(schedule_lists=wait, abort_ids=aborts, control_cmd=cmds[-1])
         else:
-            pkg = IPCPackage(schedule_lists=self.wait_lists, abort_ids=self.abort_ids)
+            pkg = IPCPackage(schedule_lists=wait, abort_ids=aborts)
         self._post(pkg)
-        self.wait_lists, self.abort_ids, self.control_cmds = [], [], []
 
     def _post(self, pkg: IPCPackage):
         if self.worker is not None:
@@ -270,7 +281,8 @@ class LLM:
             if seq is not None:
                 seq.finish_time = now
                 self.finished.append(seq)
-            self.id_allocator.free(sid)
+            with self._inbox_lock:
+                self.id_allocator.free(sid)
         if pkg.stats:
             self.last_stats = pkg.stats
 
@@ -388,7 +400,8 @@ class LLM:
 
     # -------------------------------------------------------------------------------------------
     def send_control_command(self, cmd: tuple):
-        self.control_cmds.append(cmd)
+        with self._inbox_lock:
+            self.control_cmds.append(cmd)
 
     def start_profile(self):
         self.send_control_command(("start_profile",))

@@ -375,3 +375,37 @@ def test_random_arrivals_and_aborts_through_the_engine(async_schedule):
         assert not llm.running_maps
         assert llm.id_allocator.get_num_free_ids() == 100000 - 0                  # every sequence id returned
         llm.shutdown()
+
+
+def test_requests_submitted_from_another_thread_are_never_lost():
+    """The API server adds requests from the event-loop thread while the engine tick runs in a worker thread: a
+    request arriving in the middle of `_send` must neither vanish nor lose its tokens."""
+    import threading
+    import random
+    from gllm_b200 import LLM
+    from gllm_b200.models.presets import tiny
+    cfg = tiny("Qwen3ForCausalLM", num_hidden_layers=1, max_position_embeddings=256)
+    llm = LLM(cfg, load_format="dummy", maxp=64, maxd=64, num_cpu_pages=512, page_size=4, log_stats=False, device="cpu")
+    n = 400
+    seqs = []
+    rng = random.Random(0)
+
+    def feeder():
+        for i in range(n):
+            s = llm.allocate_seq([5 + i % 50, 7, 9], 1 + i % 3, True, top_k=1)
+            seqs.append(s)
+            llm.add_requests([s])
+            if i % 7 == 0:
+                time.sleep(rng.random() * 0.0005)
+
+    import time
+    th = threading.Thread(target=feeder)
+    th.start()
+    t0 = time.time()
+    while len(llm.finished) < n:
+        llm.schedule()
+        assert time.time() - t0 < 120, f"only {len(llm.finished)} of {n} requests finished: some were lost"
+    th.join()
+    assert all(s.num_output_tokens == s.output_len for s in seqs)
+    assert not llm.running_maps and llm.id_allocator.get_num_free_ids() == 100000
+    llm.shutdown()

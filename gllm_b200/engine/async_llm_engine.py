@@ -154,6 +154,8 @@ class AsyncLLM(LLM):
         async_llm_engine.py:93-97 polls `is_disconnected` from the engine task; here the request's own
         task reports it, which also works under ASGI test transports)."""
         seq = self.running_maps.get(stream.seq_id)
+        if seq is None:      # accepted but not handed to the engine yet (the tick thread has not run `_send`)
+            seq = next((s for s in list(self.wait_lists) if s.seq_id == stream.seq_id), None)
         if seq is not None and not seq.is_abort and not stream.finished:
             self.abort([stream.seq_id])
             seq.is_abort = True

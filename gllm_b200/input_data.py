@@ -60,6 +60,7 @@ class BatchArrays:
     feed_src: Optional[np.ndarray] = None
     emit_ids: Optional[list] = None  # driver-local: sequence id per EMITTING entry (order of the sampler output)
     seq_ids: Optional[list] = None  # driver-local: sequence id per row (incremental decode batches); not sent
+    pt_gens: Optional[list] = None  # driver-local: Sequence.pt_gen per row when the block table rows were written
     seq_index: Optional[dict] = None  # driver-local: seq id -> row (built lazily by the next batch)
 
     def is_decode_only(self) -> bool:
@@ -129,8 +130,8 @@ def _build_decode_fast(entries, page_size: int, batch_id: int, prev: "BatchArray
         where = {sid: i for i, sid in enumerate(prev.seq_ids)}
         prev.seq_index = where
     try:   # one pass over the entries: (previous row, position, token, seq id)
-        data = [(where[e.seq.seq_id], e.start, e.seq.token_ids[e.start], e.seq.seq_id) if e.n == 1 and e.emits
-                else None for e in entries]
+        data = [(where[e.seq.seq_id], e.start, e.seq.token_ids[e.start], e.seq.seq_id, e.seq.pt_gen)
+                if e.n == 1 and e.emits else None for e in entries]
         arr = np.array(data, dtype=np.int64)
     except (KeyError, TypeError, ValueError):
         return None
@@ -140,7 +141,12 @@ def _build_decode_fast(entries, page_size: int, batch_id: int, prev: "BatchArray
     starts = arr[:, 1].astype(np.int32)
     tokens = arr[:, 2].astype(np.int32)
     ids = arr[:, 3].tolist()
+    gens = arr[:, 4].tolist()
     if not np.array_equal(starts, prev.positions[perm] + 1):
+        return None
+    # a sequence that was preempted and whose recompute ends in a 1-token tail looks like a decode row, but its
+    # page table was rebuilt (other physical pages, e.g. prefix-cache hits): the previous block-table row is stale
+    if prev.pt_gens is None or [prev.pt_gens[i] for i in perm.tolist()] != gens:
         return None
     blk = starts // page_size
     bt = prev.block_table[perm]              # fancy indexing: a new array
@@ -159,7 +165,7 @@ def _build_decode_fast(entries, page_size: int, batch_id: int, prev: "BatchArray
         temperature=prev.temperature[perm], top_k=prev.top_k[perm], top_p=prev.top_p[perm],
         rep_penalty=prev.rep_penalty[perm], state_slot=prev.state_slot[perm], num_decode_seqs=b, num_seqs=b, num_tokens=b, max_q_len=1,
         max_seq_len=int(seq_lens.max()), all_greedy=prev.all_greedy, need_penalty=False, batch_id=batch_id,
-        seq_ids=ids, emit_ids=ids)
+        seq_ids=ids, emit_ids=ids, pt_gens=gens)
 
 
 def build_batch(entries, page_size: int, vocab_size: int, batch_id: int = 0, mrope: bool = False,
@@ -254,6 +260,7 @@ def build_batch(entries, page_size: int, vocab_size: int, batch_id: int = 0, mro
         seen_tokens=np.concatenate(seen_tokens) if seen_tokens else None,
         clear_slots=np.asarray(clear_slots, dtype=np.int32) if clear_slots else None, batch_id=batch_id, mm=mm,
         seq_ids=[e.seq.seq_id for e in entries] if n_dec == b else None,
+        pt_gens=[e.seq.pt_gen for e in entries] if n_dec == b else None,
         emit_ids=[entries[i].seq.seq_id for i in emit_seq])
 
 

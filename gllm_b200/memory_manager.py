@@ -72,6 +72,7 @@ class MemoryManager:
             self.free_page(page)
         seq.page_table = []
         seq.pt_np = None
+        seq.pt_gen += 1
         seq.page_hashes = []
 
     def get_num_free_pages(self) -> int:

@@ -9,7 +9,7 @@ class Sequence:
                  "finish_tokens", "output_len", "cur_length", "temperature", "top_p", "top_k",
                  "repetition_penalty", "computed_token_num", "scheduled_token_num", "is_abort",
                  "mm_contents", "page_hashes", "num_cached_tokens", "arrival_time", "first_token_time",
-                 "finish_time", "slot", "mrope_delta", "mm_state", "pt_np", "pending", "zombie")
+                 "finish_time", "slot", "mrope_delta", "mm_state", "pt_np", "pending", "zombie", "pt_gen")
 
     def __init__(self, seq_id: int, token_ids: List[int], finish_tokens: List[int],
                  output_len: Optional[int] = None, ignore_eos: bool = False, temperature: float = 0.6,
@@ -43,6 +43,8 @@ class Sequence:
         self.slot = -1  # row in the persistent per-sequence device state (penalty bitmask, ...)
         self.mrope_delta = 0
         self.pt_np = None  # numpy mirror of page_table (rebuilt only when its length changes)
+        self.pt_gen = 0    # bumped whenever the page table is rebuilt from scratch (preemption): rows derived from
+                           # an earlier table (incremental batch assembly) are stale then
         self.pending = -1    # index of a placeholder token reserved by a lookahead step (async scheduling)
         self.zombie = False  # finished while a lookahead step was already in flight: pages freed when it returns
         self.mm_state = None
@@ -81,6 +83,7 @@ class Sequence:
         self.scheduled_token_num = 0
         self.page_table = []
         self.pt_np = None
+        self.pt_gen += 1
         self.page_hashes = []
         if self.mm_state:
             self.mm_state["sent"] = False  # the vision embeddings must be recomputed too

@@ -7,14 +7,14 @@ import numpy as np
 import pytest
 
 hypothesis = pytest.importorskip("hypothesis")
-from hypothesis import HealthCheck, given, settings, strategies as st  # noqa: E402
+from hypothesis import HealthCheck, example, given, settings, strategies as st  # noqa: E402
 
 from gllm_b200.input_data import build_batch  # noqa: E402
 from gllm_b200.memory_manager import PrefixMemoryManager  # noqa: E402
 from gllm_b200.scheduler import Scheduler  # noqa: E402
 from gllm_b200.sequence import Sequence  # noqa: E402
 
-PAGE = 4
+PAGE = int(__import__("os").environ.get("GLLM_HYP_PAGE", "4"))
 
 
 def check_invariants(mm: PrefixMemoryManager, live):
@@ -46,8 +46,12 @@ def check_invariants(mm: PrefixMemoryManager, live):
 @given(seed=st.integers(0, 10 ** 6), n_req=st.integers(1, 14), pages=st.integers(10, 40),
        method=st.sampled_from(["chunked_prefill", "token_throttling", "split_pd"]),
        maxp=st.sampled_from([8, 16, 64]), abort_rate=st.sampled_from([0.0, 0.1]), pp=st.sampled_from([1, 2]),
-       kvthresh=st.sampled_from([0.0, 0.1, 0.3]))
-def test_random_streams_keep_kv_bookkeeping_consistent(seed, n_req, pages, method, maxp, abort_rate, pp, kvthresh):
+       kvthresh=st.sampled_from([0.0, 0.1, 0.3]), page=st.sampled_from([2, 4]))
+@example(seed=185, n_req=10, pages=10, method="split_pd", maxp=8, abort_rate=0.1, pp=1, kvthresh=0.0, page=2)
+def test_random_streams_keep_kv_bookkeeping_consistent(seed, n_req, pages, method, maxp, abort_rate, pp, kvthresh,
+                                                       page):
+    global PAGE
+    PAGE = page       # small pages: preemption + prefix-cache hits + page-boundary cases every few tokens
     rng = random.Random(seed)
     mm = PrefixMemoryManager(pages, PAGE)
     sch = Scheduler(mm, pp_size=pp, world_size=pp, schedule_method=method, maxd=6, maxp=maxp, minp=4, iterp=2,

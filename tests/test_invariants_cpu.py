@@ -128,6 +128,18 @@ def _tok(seq_id: int, pos: int) -> int:
     return 3 + (seq_id * 7919 + pos * 104729) % 45
 
 
+def _check_incremental(entries, prev_arrays):
+    """The worker builds every batch with `prev=` the previous one: the incremental result must equal a full build."""
+    inc = build_batch(entries, PAGE, 64, 0, prev=prev_arrays)
+    full = build_batch(entries, PAGE, 64, 0, prev=None)
+    for name in ("tokens", "positions", "slot_mapping", "seq_lens", "query_start_loc", "logits_idx"):
+        assert np.array_equal(getattr(inc, name), getattr(full, name)), name
+    for r in range(len(entries)):
+        nblk = (int(full.seq_lens[r]) + PAGE - 1) // PAGE
+        assert np.array_equal(inc.block_table[r, :nblk], full.block_table[r, :nblk])
+    return inc
+
+
 def _drive(reqs_spec, pages, method, maxp, lookahead, arrivals, abort_plan):
     """Emulates the driver loop of engine/worker.py (run_driver) around the real Scheduler."""
     mm = PrefixMemoryManager(pages, PAGE)
@@ -138,6 +150,7 @@ def _drive(reqs_spec, pages, method, maxp, lookahead, arrivals, abort_plan):
     inflight = []            # launched batches whose tokens are not back yet (<= 2 with lookahead)
     produced = {}
     n_look = 0
+    prev_arrays = None
     for step in range(3000):
         if pending_reqs and arrivals[step % len(arrivals)]:
             sch.add_new_requests([pending_reqs.pop(0)])
@@ -149,6 +162,7 @@ def _drive(reqs_spec, pages, method, maxp, lookahead, arrivals, abort_plan):
             if look:
                 n_look += 1
                 inflight.append(look)
+                prev_arrays = _check_incremental(look, prev_arrays)
         keep = 1 if (lookahead and len(inflight) == 2) else 0
         while len(inflight) > keep:
             done = inflight.pop(0)
@@ -163,6 +177,7 @@ def _drive(reqs_spec, pages, method, maxp, lookahead, arrivals, abort_plan):
         entries = sch.schedule_once()
         if entries:
             inflight.append(entries)
+            prev_arrays = _check_incremental(entries, prev_arrays)
         if not pending_reqs and not sch.has_work() and not inflight:
             break
     assert not pending_reqs and not sch.has_work() and not inflight, "engine did not drain"
@@ -176,8 +191,10 @@ def _drive(reqs_spec, pages, method, maxp, lookahead, arrivals, abort_plan):
           derandomize=not __import__("os").environ.get("GLLM_HYP_RANDOM"), suppress_health_check=[HealthCheck.too_slow])
 @given(seed=st.integers(0, 10 ** 6), n_req=st.integers(1, 10), pages=st.integers(12, 48),
        method=st.sampled_from(["chunked_prefill", "token_throttling"]), maxp=st.sampled_from([8, 16, 64]),
-       aborts=st.booleans())
-def test_lookahead_scheduling_equals_synchronous(seed, n_req, pages, method, maxp, aborts):
+       aborts=st.booleans(), page=st.sampled_from([2, 4]))
+def test_lookahead_scheduling_equals_synchronous(seed, n_req, pages, method, maxp, aborts, page):
+    global PAGE
+    PAGE = page
     """Async (lookahead) scheduling — placeholder tokens, zombies, pages reserved one step ahead — must give every
     request exactly the tokens the synchronous loop gives it and leave no page behind."""
     rng = random.Random(seed)

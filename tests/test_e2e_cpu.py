@@ -336,12 +336,17 @@ def test_random_arrivals_and_aborts_through_the_engine(async_schedule):
     cfg = tiny("Qwen3ForCausalLM", num_hidden_layers=1, max_position_embeddings=512)
 
     def engine():
-        return LLM(cfg, load_format="dummy", maxp=24, maxd=6, num_cpu_pages=96, page_size=4, log_stats=False,
+        return LLM(cfg, load_format="dummy", maxp=24, maxd=6, num_cpu_pages=pool, page_size=4, log_stats=False,
                    device="cpu", kvthresh=0.0, async_schedule=async_schedule, enable_prefix_caching=True, seed=0)
 
     for seed in range(int(os.environ.get("GLLM_CHURN_SEEDS", "4"))):
         rng = random.Random(seed)
-        prompts = [[rng.randrange(5, 300) for _ in range(rng.randrange(1, 30))] for _ in range(14)]
+        pool = (96, 40, 28)[seed % 3]        # roomy / tight / very tight KV pool (preemption + recompute)
+        stems = [[rng.randrange(5, 300) for _ in range(rng.randrange(4, 24))] for _ in range(3)]   # shared prefixes
+        prompts = []
+        for _ in range(14):
+            st_ = rng.choice(stems)
+            prompts.append(st_[:rng.randrange(1, len(st_) + 1)] + [rng.randrange(5, 300) for _ in range(rng.randrange(0, 8))])
         outs = [rng.randrange(1, 14) for _ in prompts]
         llm = engine()
         quiet = [s.token_ids for s in llm.generate(tokens=prompts, output_lens=outs, ignore_eos=True)]

@@ -65,10 +65,10 @@ class _RowLinear(nn.Linear):
         self.tp = tp
 
     def forward(self, x):
-        y = F.linear(x, self.weight)
-        if self.tp[1] > 1:
-            from gllm_b200.parallel import state as ps
-            y = ps.tp_all_reduce(y)
+        if self.tp[1] == 1:
+            return F.linear(x, self.weight, self.bias)     # unsharded: exactly nn.Linear (bias fused in the GEMM)
+        from gllm_b200.parallel import state as ps
+        y = ps.tp_all_reduce(F.linear(x, self.weight))
         return y if self.bias is None else y + self.bias
 
 

@@ -294,3 +294,40 @@ def test_reference_sampler_draws_inside_the_filtered_support(seed, b, v, k, p, t
         if kept.sum() > 1:
             smallest = float(base[r][kept].min())
             assert mass_kept - smallest < p + 1e-4              # dropping the weakest kept token would fall short
+
+
+@settings(max_examples=100, deadline=None, derandomize=True)
+@given(seed=st.integers(0, 10 ** 6), b=st.integers(1, 9), mrope=st.booleans(), penalty=st.booleans(),
+       feed=st.booleans(), mm=st.booleans())
+def test_batch_wire_round_trip(seed, b, mrope, penalty, feed, mm):
+    """Every field a peer needs survives Comm's single-buffer encoding (optional arrays, 2-D positions, the
+    multimodal payload dict), bit for bit, for arbitrary shapes."""
+    from gllm_b200.engine.comm import Comm
+    from gllm_b200.input_data import BatchArrays
+    rng = np.random.default_rng(seed)
+    q = rng.integers(1, 7, b).astype(np.int32)
+    t = int(q.sum())
+    i32 = lambda *shape: rng.integers(0, 1000, shape).astype(np.int32)    # noqa: E731
+    f32 = lambda *shape: rng.random(shape).astype(np.float32)             # noqa: E731
+    batch = BatchArrays(
+        tokens=i32(t), positions=i32(3, t) if mrope else i32(t), slot_mapping=i32(t),
+        block_table=i32(b, int(rng.integers(1, 9))), seq_lens=i32(b), query_start_loc=np.concatenate([[0], q.cumsum()]).astype(np.int32),
+        logits_idx=i32(b), emit_seq=np.arange(b, dtype=np.int32), temperature=f32(b), top_k=i32(b), top_p=f32(b),
+        rep_penalty=f32(b), state_slot=i32(b), num_decode_seqs=int(rng.integers(0, b + 1)), num_seqs=b, num_tokens=t,
+        max_q_len=int(q.max()), max_seq_len=77, all_greedy=not penalty, need_penalty=penalty, batch_id=seed % 1000,
+        seen_rows=i32(5) if penalty else None, seen_tokens=i32(5) if penalty else None,
+        clear_slots=i32(2) if penalty else None, feed_src=i32(b) if feed else None,
+        mm={"rows": [1, 2], "pixel_values": f32(6, 10), "grid": [[1, 2, 3]]} if mm else None)
+    got = Comm._decode_batch(memoryview(Comm._encode_batch(batch)))
+    for name in ("tokens", "positions", "slot_mapping", "block_table", "seq_lens", "query_start_loc", "logits_idx",
+                 "emit_seq", "temperature", "top_k", "top_p", "rep_penalty", "state_slot", "seen_rows", "seen_tokens",
+                 "clear_slots", "feed_src"):
+        a, g = getattr(batch, name), getattr(got, name)
+        assert (a is None and g is None) or (a.dtype == g.dtype and a.shape == g.shape and np.array_equal(a, g)), name
+    for name in ("num_decode_seqs", "num_seqs", "num_tokens", "max_q_len", "max_seq_len", "all_greedy", "need_penalty",
+                 "batch_id"):
+        assert getattr(batch, name) == getattr(got, name), name
+    if mm:
+        assert got.mm["rows"] == [1, 2] and np.array_equal(got.mm["pixel_values"], batch.mm["pixel_values"])
+    else:
+        assert got.mm is None

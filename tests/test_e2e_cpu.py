@@ -414,3 +414,80 @@ def test_requests_submitted_from_another_thread_are_never_lost():
     assert all(s.num_output_tokens == s.output_len for s in seqs)
     assert not llm.running_maps and llm.id_allocator.get_num_free_ids() == 100000
     llm.shutdown()
+
+
+def test_random_dense_configs_match_hf():
+    """Loader / spec robustness: randomly drawn dense configurations (GQA ratios incl. MQA, head_dim != hidden /
+    heads, tied embeddings, attention biases, odd intermediate sizes, page sizes, chunk sizes) stay token-exact
+    against HuggingFace."""
+    import random
+    from transformers import LlamaConfig, LlamaForCausalLM, Qwen2Config, Qwen2ForCausalLM, Qwen3Config, Qwen3ForCausalLM
+    n = int(os.environ.get("GLLM_CFG_SEEDS", "5"))
+    for seed in range(n):
+        rng = random.Random(seed)
+        torch.manual_seed(100 + seed)
+        heads = rng.choice([2, 4, 8])
+        kv = rng.choice([h for h in (1, 2, 4, 8) if h <= heads and heads % h == 0])
+        hd = rng.choice([16, 32])
+        fam = rng.choice(["llama", "qwen2", "qwen3"])
+        common = dict(hidden_size=rng.choice([64, 96, 128]), intermediate_size=rng.choice([80, 128, 176]),
+                      num_hidden_layers=rng.choice([1, 2, 3]), num_attention_heads=heads, num_key_value_heads=kv,
+                      vocab_size=rng.choice([320, 512, 777]), max_position_embeddings=512, eos_token_id=1,
+                      tie_word_embeddings=rng.random() < 0.5, rms_norm_eps=rng.choice([1e-5, 1e-6]))
+        if fam == "llama":
+            cfg = LlamaConfig(**common, head_dim=hd, attention_bias=rng.random() < 0.3)
+            model = LlamaForCausalLM(cfg)
+        elif fam == "qwen2":
+            common["hidden_size"] = heads * hd        # Qwen2 has no explicit head_dim
+            cfg = Qwen2Config(**common)
+            model = Qwen2ForCausalLM(cfg)
+        else:
+            cfg = Qwen3Config(**common, head_dim=hd)
+            model = Qwen3ForCausalLM(cfg)
+        model = model.eval().float()
+        try:
+            _check(model, page_size=rng.choice([4, 8, 16]), maxp=rng.choice([16, 48, 64]),
+                   enable_prefix_caching=rng.random() < 0.5)
+        except AssertionError as e:
+            raise AssertionError(f"seed {seed}: {fam} {cfg.to_dict()}") from e
+
+
+def test_random_moe_configs_match_hf():
+    """Same idea for the MoE families: expert counts that are not multiples of 8 (router padding), top-k, shared
+    experts, renormalisation, sparse-step / mlp-only layer patterns."""
+    import random
+    from transformers import (MixtralConfig, MixtralForCausalLM, Qwen2MoeConfig, Qwen2MoeForCausalLM, Qwen3MoeConfig,
+                              Qwen3MoeForCausalLM)
+    n = int(os.environ.get("GLLM_CFG_SEEDS", "4"))
+    for seed in range(n):
+        rng = random.Random(1000 + seed)
+        torch.manual_seed(200 + seed)
+        heads = rng.choice([2, 4])
+        kv = rng.choice([h for h in (1, 2, 4) if h <= heads and heads % h == 0])
+        experts = rng.choice([3, 4, 6, 8])
+        topk = rng.randrange(1, min(experts, 3) + 1)
+        layers = rng.choice([2, 3])
+        fam = rng.choice(["mixtral", "qwen2_moe", "qwen3_moe"])
+        base = dict(hidden_size=64, num_hidden_layers=layers, num_attention_heads=heads, num_key_value_heads=kv,
+                    vocab_size=512, max_position_embeddings=512, eos_token_id=1, tie_word_embeddings=False)
+        if fam == "mixtral":
+            cfg = MixtralConfig(**base, intermediate_size=rng.choice([64, 96]), num_local_experts=experts,
+                                num_experts_per_tok=topk)
+            model = MixtralForCausalLM(cfg)
+        elif fam == "qwen2_moe":
+            cfg = Qwen2MoeConfig(**base, intermediate_size=96, moe_intermediate_size=rng.choice([32, 48]),
+                                 shared_expert_intermediate_size=rng.choice([32, 64]), num_experts=experts,
+                                 num_experts_per_tok=topk, norm_topk_prob=rng.random() < 0.5,
+                                 decoder_sparse_step=rng.choice([1, 2]),
+                                 mlp_only_layers=[0] if rng.random() < 0.3 else [])
+            model = Qwen2MoeForCausalLM(cfg)
+        else:
+            cfg = Qwen3MoeConfig(**base, head_dim=16, intermediate_size=96, moe_intermediate_size=rng.choice([32, 48]),
+                                 num_experts=experts, num_experts_per_tok=topk, norm_topk_prob=rng.random() < 0.5,
+                                 decoder_sparse_step=rng.choice([1, 2]), mlp_only_layers=[])
+            model = Qwen3MoeForCausalLM(cfg)
+        model = model.eval().float()
+        try:
+            _check(model, page_size=rng.choice([8, 16]), maxp=rng.choice([32, 64]))
+        except AssertionError as e:
+            raise AssertionError(f"seed {seed}: {fam} {cfg.to_dict()}") from e

@@ -491,3 +491,35 @@ def test_random_moe_configs_match_hf():
             _check(model, page_size=rng.choice([8, 16]), maxp=rng.choice([32, 64]))
         except AssertionError as e:
             raise AssertionError(f"seed {seed}: {fam} {cfg.to_dict()}") from e
+
+
+def test_random_deepseek_v3_configs_match_hf():
+    """MLA + grouped routing under randomly drawn shapes: with / without the q LoRA, different nope / rope / v head
+    sizes, group counts, dense-prefix depth, shared-expert counts, routing scale."""
+    import random
+    from transformers import DeepseekV3Config, DeepseekV3ForCausalLM
+    n = int(os.environ.get("GLLM_CFG_SEEDS", "3"))
+    for seed in range(n):
+        rng = random.Random(2000 + seed)
+        torch.manual_seed(300 + seed)
+        groups = rng.choice([1, 2, 4])
+        experts = groups * rng.choice([2, 3])
+        topk_group = rng.randrange(1, groups + 1)
+        topk = rng.randrange(1, min(4, topk_group * (experts // groups)) + 1)
+        cfg = DeepseekV3Config(
+            hidden_size=64, intermediate_size=96, moe_intermediate_size=rng.choice([32, 48]),
+            num_hidden_layers=rng.choice([2, 3]), num_attention_heads=rng.choice([2, 4]), num_key_value_heads=4,
+            n_routed_experts=experts, n_shared_experts=rng.choice([1, 2]), num_experts_per_tok=topk, n_group=groups,
+            topk_group=topk_group, first_k_dense_replace=rng.choice([0, 1]), routed_scaling_factor=rng.choice([1.0, 2.5]),
+            norm_topk_prob=rng.random() < 0.7, q_lora_rank=rng.choice([None, 24]), kv_lora_rank=rng.choice([16, 32]),
+            qk_nope_head_dim=rng.choice([16, 32]), qk_rope_head_dim=rng.choice([8, 16]), v_head_dim=rng.choice([16, 32]),
+            vocab_size=512, max_position_embeddings=512, eos_token_id=1, rope_scaling=None, rope_interleave=True)
+        cfg.num_key_value_heads = cfg.num_attention_heads
+        m = DeepseekV3ForCausalLM(cfg).eval().float()
+        for name, b in list(m.named_buffers()) + list(m.named_parameters()):
+            if "e_score_correction_bias" in name:
+                b.data.normal_(std=0.05)
+        try:
+            _check(m, page_size=rng.choice([8, 16]))
+        except AssertionError as e:
+            raise AssertionError(f"seed {seed}: {cfg.to_dict()}") from e

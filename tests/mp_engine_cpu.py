@@ -18,7 +18,8 @@ def main():
     over = {}
     if arch == "MixtralForCausalLM":
         over = dict(num_local_experts=4, num_experts_per_tok=2)
-    cfg = tiny(arch, num_hidden_layers=4, **over)
+    over.update(json.loads(os.environ.get("GLLM_TEST_CFG", "{}")))     # shape overrides for sharding edge cases
+    cfg = tiny(arch, **{"num_hidden_layers": 4, **over})
     torch.manual_seed(0)
     llm = LLM(cfg, load_format="dummy", pp_size=pp, tp_size=tp, maxp=48, maxd=16, num_cpu_pages=128,
               model_max_length=256, log_stats=False, device="cpu", launch_mode="inproc", schedule_method=method,

@@ -99,3 +99,13 @@ def test_shared_memory_batch_ring_matches_single(single, monkeypatch, pp, tp, po
     shared-memory broadcast ring instead of ZeroMQ sockets."""
     monkeypatch.setenv("GLLM_BATCH_TRANSPORT", "shm")
     assert _run(pp, tp, port=port) == single
+
+
+def test_tp2_sharding_edge_shapes_match_single(monkeypatch):
+    """Multi-query attention (1 KV head replicated on both ranks), a vocabulary that is not a multiple of the
+    shard padding, tied embeddings, an odd intermediate size: TP2 == single process."""
+    monkeypatch.setenv("GLLM_TEST_CFG", json.dumps({"num_key_value_heads": 1, "vocab_size": 777,
+                                                    "tie_word_embeddings": True, "intermediate_size": 264}))
+    ref_tokens = _run(1, 1)
+    assert _run(1, 2, port=29941) == ref_tokens
+    assert _run(2, 2, port=29951) == ref_tokens      # tied embeddings live on the first AND the last stage

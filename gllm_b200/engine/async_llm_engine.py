@@ -128,6 +128,7 @@ class AsyncLLM(LLM):
         self.async_streams: Dict[int, AsyncStream] = {}
         self._task: Optional[asyncio.Task] = None
         self._pending_tokens: List = []
+        self.failed: Optional[str] = None      # set when the engine loop died: the server answers 500 from then on
         self.metrics = {"requests_total": 0, "requests_finished": 0, "requests_aborted": 0,
                         "prompt_tokens_total": 0, "generation_tokens_total": 0, "ttft_sum": 0.0, "ttft_count": 0}
         self.hist = {"ttft": Histogram(TTFT_BUCKETS), "tpot": Histogram(TPOT_BUCKETS),
@@ -145,7 +146,7 @@ class AsyncLLM(LLM):
         self.metrics["requests_total"] += 1
         self.metrics["prompt_tokens_total"] += len(token_ids)
         self.add_requests([seq])
-        if self._task is None:
+        if self._task is None and self.failed is None:
             self.start_schedule_engine()
         return stream
 
@@ -244,6 +245,7 @@ class AsyncLLM(LLM):
             except Exception as e:  # noqa: BLE001
                 logger.error("engine background task failed: %r", e, exc_info=e)
                 # fail-stop: release every waiting client instead of hanging them
+                self.failed = repr(e)
                 for st in list(self.async_streams.values()):
                     st._queue.put_nowait(RuntimeError(f"engine failure: {e!r}"))
                 self.async_streams.clear()

@@ -203,6 +203,8 @@ class LLM:
                      top_k=None, repetition_penalty=None, mm_contents=None) -> Sequence:
         """Defaults: temperature/top_p/repetition_penalty from generation_config, top_k = 1
         (greedy) unless given (reference: gllm/llm_engine.py:305-337)."""
+        if len(token_ids) == 0:
+            raise ValueError("empty prompt: there is no position to sample the first token from")
         with self._inbox_lock:      # ids are freed by the tick thread (`_apply`)
             sid = self.id_allocator.allocate()
         seq = Sequence(sid, token_ids, self.finish_tokens, output_len, ignore_eos,

@@ -35,6 +35,30 @@ def _error(msg: str, status=HTTPStatus.BAD_REQUEST):
                         status_code=status.value)
 
 
+def _validate_sampling(request):
+    if request.temperature is not None and request.temperature < 0:
+        return "temperature must be >= 0"
+    if request.top_p is not None and not 0.0 < request.top_p <= 1.0:
+        return "top_p must be in (0, 1]"
+    if request.repetition_penalty is not None and request.repetition_penalty <= 0:
+        return "repetition_penalty must be > 0"
+    return None
+
+
+def _validate(token_ids, output_len, vocab_size=None):
+    """-> error message or None. An empty prompt or a token id outside the vocabulary would take the whole engine
+    down (there is no row to sample from / the embedding lookup faults), so they are refused at the door."""
+    if not token_ids:
+        return "the prompt is empty"
+    if output_len is not None and output_len < 1:
+        return "max_tokens must be at least 1"
+    if vocab_size is not None and (min(token_ids) < 0 or max(token_ids) >= vocab_size):
+        return f"token ids must be in [0, {vocab_size})"
+    if not llm.check_seq_length(token_ids, output_len):
+        return "seq length exceeds max model length"
+    return None
+
+
 def _usage(stream) -> UsageInfo:
     return UsageInfo(prompt_tokens=stream.prompt_tokens, completion_tokens=stream.completion_tokens,
                      total_tokens=stream.prompt_tokens + stream.completion_tokens)
@@ -128,6 +152,8 @@ def build_app(engine):
     @app.get("/health")
     async def health():
         llm.check_worker_alive()
+        if llm.failed:
+            return JSONResponse({"status": "engine failure", "detail": llm.failed}, status_code=500)
         return JSONResponse({"status": "ok"})
 
     @app.get("/metrics")
@@ -174,8 +200,12 @@ def build_app(engine):
                 token_ids = await _in_thread(llm.encode, None, True, request.messages)
         except Exception as e:  # noqa: BLE001
             return _error(f"cannot encode messages: {e}")
-        if not llm.check_seq_length(token_ids, request.output_len()):
-            return _error("seq length exceeds max model length")
+        bad = _validate_sampling(request) or _validate(token_ids, request.output_len(),
+                                                       llm.loader.config.get("vocab_size"))
+        if bad:
+            return _error(bad)
+        if llm.failed:
+            return _error(f"engine is down: {llm.failed}", HTTPStatus.INTERNAL_SERVER_ERROR)
         stream = await llm.add_requests_async(raw_request, token_ids, request.output_len(), request.ignore_eos,
                                               request.temperature, request.top_p, request.top_k,
                                               request.repetition_penalty, mm_contents, stop=request.stop)
@@ -190,8 +220,12 @@ def build_app(engine):
             token_ids = await _in_thread(_encode_prompt, request.prompt)
         except Exception as e:  # noqa: BLE001
             return _error(f"cannot encode prompt: {e}")
-        if not llm.check_seq_length(token_ids, request.max_tokens):
-            return _error("seq length exceeds max model length")
+        bad = _validate_sampling(request) or _validate(token_ids, request.max_tokens,
+                                                       llm.loader.config.get("vocab_size"))
+        if bad:
+            return _error(bad)
+        if llm.failed:
+            return _error(f"engine is down: {llm.failed}", HTTPStatus.INTERNAL_SERVER_ERROR)
         stream = await llm.add_requests_async(raw_request, token_ids, request.max_tokens, request.ignore_eos,
                                               request.temperature, request.top_p, request.top_k,
                                               request.repetition_penalty, stop=request.stop)

@@ -162,3 +162,34 @@ def test_stop_strings(client):
                 chunks.append(json.loads(line[6:]))
     assert "".join(ch["choices"][0]["text"] for ch in chunks) == full[:full.find(stop)]
     assert chunks[-1]["choices"][0]["finish_reason"] == "stop"
+
+
+def test_malformed_requests_are_refused_and_do_not_hurt_the_engine(client):
+    """Empty prompts, non-positive budgets, out-of-vocabulary ids and nonsensical sampling parameters get a 400;
+    none of them may reach the engine (an empty prompt used to take the whole engine loop down)."""
+    c, engine = client
+    bad = [
+        ("/v1/completions", {"prompt": "", "max_tokens": 4}),
+        ("/v1/completions", {"prompt": [[]], "max_tokens": 4}),
+        ("/v1/completions", {"prompt": [], "max_tokens": 4}),
+        ("/v1/completions", {"prompt": "hello", "max_tokens": 0}),
+        ("/v1/completions", {"prompt": "hello", "max_tokens": -3}),
+        ("/v1/completions", {"prompt": [9999999], "max_tokens": 4}),
+        ("/v1/completions", {"prompt": [-1], "max_tokens": 4}),
+        ("/v1/completions", {"prompt": "hello", "max_tokens": 100000}),
+        ("/v1/completions", {"prompt": "hello", "max_tokens": 4, "temperature": -1.0}),
+        ("/v1/completions", {"prompt": "hello", "max_tokens": 4, "top_p": 0.0}),
+        ("/v1/completions", {"prompt": "hello", "max_tokens": 4, "repetition_penalty": 0.0}),
+        ("/v1/chat/completions", {"messages": [], "max_tokens": 4}),
+        ("/v1/chat/completions", {"messages": [{"role": "user", "content": "hello"}], "max_completion_tokens": 0}),
+    ]
+    before = engine.metrics["requests_total"]
+    for url, body in bad:
+        r = c.post(url, json=body)
+        assert r.status_code == 400 and r.json()["object"] == "error", (url, body, r.status_code, r.text[:200])
+    assert engine.metrics["requests_total"] == before and engine.failed is None
+    ok = c.post("/v1/completions", json={"prompt": "hello world", "max_tokens": 3, "stop": ["", "zzz"]})
+    assert ok.status_code == 200 and ok.json()["usage"]["completion_tokens"] == 3
+    assert c.get("/health").status_code == 200
+    with pytest.raises(ValueError):
+        engine.allocate_seq([], 4)

@@ -205,6 +205,9 @@ class LLM:
         (greedy) unless given (reference: gllm/llm_engine.py:305-337)."""
         if len(token_ids) == 0:
             raise ValueError("empty prompt: there is no position to sample the first token from")
+        vocab = self.loader.config.get("vocab_size")
+        if vocab is not None and (min(token_ids) < 0 or max(token_ids) >= vocab):
+            raise ValueError(f"token ids must be in [0, {vocab}) (the embedding lookup would fault on the device)")
         with self._inbox_lock:      # ids are freed by the tick thread (`_apply`)
             sid = self.id_allocator.allocate()
         seq = Sequence(sid, token_ids, self.finish_tokens, output_len, ignore_eos,

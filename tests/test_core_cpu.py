@@ -494,3 +494,39 @@ def test_shm_ring_broadcast_wrap_and_flow_control():
     finally:
         r_early.close(); r_late.close(); w.close()
     assert not os.path.exists(f"/dev/shm/{name}")
+
+
+def test_incremental_detokenizer_streams_exactly_the_final_text():
+    """`Sequence.detokenize_inc` with a byte-level BPE (multi-byte characters split across tokens, random id
+    sequences with invalid UTF-8): the concatenated deltas equal the one-shot decode; only a trailing partial
+    character may still be held back."""
+    pytest.importorskip("tokenizers")
+    from tokenizers import Tokenizer, decoders, models, pre_tokenizers, trainers
+    from transformers import PreTrainedTokenizerFast
+    from gllm_b200.sequence import Sequence
+    corpus = ["hello world, how are you today?", "naïve café — déjà vu ☕ 你好世界 こんにちは",
+              "The quick brown fox jumps over the lazy dog 12345", "emoji 😀😃😄 test",
+              "tabs\tand\nnewlines  double  spaces", "Ünïcödé strings ßtraße"] * 20
+    tok = Tokenizer(models.BPE())
+    tok.pre_tokenizer = pre_tokenizers.ByteLevel(add_prefix_space=False)
+    tok.decoder = decoders.ByteLevel()
+    tok.train_from_iterator(corpus, trainers.BpeTrainer(vocab_size=400,
+                                                        initial_alphabet=pre_tokenizers.ByteLevel.alphabet()))
+    fast = PreTrainedTokenizerFast(tokenizer_object=tok)
+    rng = random.Random(0)
+    for trial in range(120):
+        text = " ".join(rng.choice(corpus) for _ in range(rng.randrange(1, 4)))
+        ids = fast.encode(text)
+        if rng.random() < 0.3:   # random ids too (invalid utf-8 byte sequences)
+            ids = [rng.randrange(0, fast.vocab_size) for _ in range(rng.randrange(1, 40))]
+        seq = Sequence(0, [1], [0], output_len=len(ids), ignore_eos=True)
+        out, i = "", 0
+        while i < len(ids):
+            k = rng.randrange(1, 4)
+            for t in ids[i:i + k]:
+                seq.append(t)
+            i += k
+            out += seq.detokenize_inc(fast)
+        full = fast.decode(ids, skip_special_tokens=True)
+        # text still held back (trailing partial character) is allowed to be missing, nothing else
+        assert full == out or (full.startswith(out) and "\ufffd" in fast.decode(ids[-4:])), (trial, full, out)

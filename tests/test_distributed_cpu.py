@@ -109,3 +109,9 @@ def test_tp2_sharding_edge_shapes_match_single(monkeypatch):
     ref_tokens = _run(1, 1)
     assert _run(1, 2, port=29941) == ref_tokens
     assert _run(2, 2, port=29951) == ref_tokens      # tied embeddings live on the first AND the last stage
+
+
+def test_pp2_explicit_layer_assignment_matches_single(single, monkeypatch):
+    """`--assigned-layers 3,1` (reference: dist_utils.py:175-209): an uneven explicit split of the 4 layers."""
+    monkeypatch.setenv("GLLM_TEST_ASSIGNED", "3,1")
+    assert _run(2, 1, port=29971) == single

@@ -24,6 +24,7 @@ def main():
     llm = LLM(cfg, load_format="dummy", pp_size=pp, tp_size=tp, maxp=48, maxd=16, num_cpu_pages=128,
               model_max_length=256, log_stats=False, device="cpu", launch_mode="inproc", schedule_method=method,
               assigned_layers=os.environ.get("GLLM_TEST_ASSIGNED") or None,
+              use_ep=os.environ.get("GLLM_TEST_NO_EP") != "1",
               seed=0, async_schedule=os.environ.get("GLLM_TEST_ASYNC") == "1",
               enable_prefix_caching=os.environ.get("GLLM_TEST_ASYNC") != "1")
     # identical weights on every layout: re-initialise from one global state dict

@@ -193,3 +193,24 @@ def test_malformed_requests_are_refused_and_do_not_hurt_the_engine(client):
     assert c.get("/health").status_code == 200
     with pytest.raises(ValueError):
         engine.allocate_seq([], 4)
+
+
+def test_disable_thinking_reaches_the_chat_template():
+    """`--disable-thinking` / `use_thinking=False` -> `enable_thinking=False` in `apply_chat_template`
+    (reference: model_runner.py:201-214)."""
+    from gllm_b200 import LLM
+    from transformers import AutoTokenizer
+    d = _make_model_dir()
+    tok = AutoTokenizer.from_pretrained(d)
+    tok.chat_template = ("{% for m in messages %}<|{{ m['role'] }}|> {{ m['content'] }} {% endfor %}"
+                         "{% if add_generation_prompt %}<|assistant|> {% if enable_thinking is defined and not "
+                         "enable_thinking %}w1 w2 {% endif %}{% endif %}")
+    tok.save_pretrained(d)
+    msgs = [{"role": "user", "content": "hello world"}]
+    ids = {}
+    for flag in (True, False):
+        llm = LLM(d, maxp=32, maxd=8, num_cpu_pages=32, model_max_length=128, log_stats=False, use_thinking=flag)
+        ids[flag] = llm.encode(None, True, msgs)
+        llm.shutdown()
+    extra = tok.encode("w1 w2", add_special_tokens=False)
+    assert ids[False][-len(extra):] == extra and ids[True] == ids[False][:-len(extra)]

@@ -115,3 +115,10 @@ def test_pp2_explicit_layer_assignment_matches_single(single, monkeypatch):
     """`--assigned-layers 3,1` (reference: dist_utils.py:175-209): an uneven explicit split of the 4 layers."""
     monkeypatch.setenv("GLLM_TEST_ASSIGNED", "3,1")
     assert _run(2, 1, port=29971) == single
+
+
+def test_mixtral_tp2_without_expert_parallelism_matches_single(monkeypatch):
+    """`--disable-ep`: every rank holds all experts with intermediate / tp columns (reference: layer.py:249-259)."""
+    ref_tokens = _run(1, 1, arch="MixtralForCausalLM")
+    monkeypatch.setenv("GLLM_TEST_NO_EP", "1")
+    assert _run(1, 2, arch="MixtralForCausalLM", port=29991) == ref_tokens

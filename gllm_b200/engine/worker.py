@@ -79,7 +79,8 @@ class Worker(ProfilerMixin):
             self.scheduler = Scheduler(self.mm, pp_size=cfg.pp_size, world_size=cfg.world_size,
                                        schedule_method=cfg.schedule_method, maxd=cfg.maxd, maxp=cfg.maxp,
                                        minp=cfg.minp, iterp=cfg.iterp, kvthresh=cfg.kvthresh,
-                                       page_size=cfg.page_size, log=cfg.log_stats)
+                                       page_size=cfg.page_size, log=cfg.log_stats,
+                                       max_seqs=cfg.max_running_seqs)
             self.slot_alloc = IDAllocator(1, max(cfg.max_running_seqs, 1))
         if self.mp_alive is not None:
             self.mp_alive[self.local_rank] = 1

@@ -89,7 +89,8 @@ class SchedulerOutput:
 class Scheduler:
     def __init__(self, memory_manager: MemoryManager, pp_size: int = 1, world_size: int = 1,
                  schedule_method: str = "chunked_prefill", maxd: int = 2048, maxp: int = 2048, minp: int = 32,
-                 iterp: int = 8, kvthresh: float = 0.05, page_size: int = 16, log: bool = True):
+                 iterp: int = 8, kvthresh: float = 0.05, page_size: int = 16, log: bool = True,
+                 max_seqs: Optional[int] = None):
         assert schedule_method in ("chunked_prefill", "split_pd", "token_throttling"), schedule_method
         self.mm = memory_manager
         self.pp_size = pp_size
@@ -98,6 +99,10 @@ class Scheduler:
         self.maxd, self.maxp, self.minp, self.iterp = maxd, maxp, minp, iterp
         self.kvthresh = kvthresh
         self.page_size = page_size
+        # capacity of the runner's per-sequence buffers (config.max_running_seqs): a micro-batch never holds more
+        # sequences. With token_throttling that capacity is maxd (as in the reference, model_runner.py:67-71) while a
+        # batch is decode rows PLUS prefill rows — without this cap a full decode batch plus one prompt overflows.
+        self.max_seqs = max_seqs
         self.num_kvthresh_pages = int(kvthresh * self.mm.get_num_free_pages())
         self.seqs_to_prefill: Deque[Sequence] = deque()
         self.seqs_to_decode: Deque[Sequence] = deque()
@@ -257,7 +262,8 @@ class Scheduler:
                                                   self.num_wait_tokens)
             else:
                 budget = min(self.maxp - len(entries), headroom)
-            prefill_batch, n_prefill = self.schedule_prefill_batch(budget)
+            room = None if self.max_seqs is None else max(self.max_seqs - len(entries), 0)
+            prefill_batch, n_prefill = self.schedule_prefill_batch(budget, room)
             entries = entries + prefill_batch
         if not entries:
             return None
@@ -354,10 +360,11 @@ class Scheduler:
         self.mm.pre_allocate_page(seqs)
         return batch
 
-    def schedule_prefill_batch(self, budget: int):
+    def schedule_prefill_batch(self, budget: int, room: Optional[int] = None):
+        """`room`: how many more sequences the micro-batch may take (None = unlimited)."""
         batch: List[ScheduledSeq] = []
         n_tokens = 0
-        while self.seqs_to_prefill and budget > 0:
+        while self.seqs_to_prefill and budget > 0 and (room is None or len(batch) < room):
             seq = self.seqs_to_prefill[0]
             if isinstance(self.mm, PrefixMemoryManager) and seq.scheduled_token_num == 0 and not seq.page_table:
                 self.mm.pre_allocate_computed_page([seq])
@@ -392,7 +399,8 @@ class Scheduler:
         budget -= len(decode_batch)
         budget = min(budget, kv_headroom_tokens(self.mm.get_num_free_pages(), self.num_kvthresh_pages,
                                                  self.page_size))
-        prefill_batch, n_prefill = self.schedule_prefill_batch(budget)
+        room = None if self.max_seqs is None else max(self.max_seqs - len(decode_batch), 0)
+        prefill_batch, n_prefill = self.schedule_prefill_batch(budget, room)
         self._log_status(num_total_decode, n_prefill, len(decode_batch))
         return decode_batch + prefill_batch
 
@@ -403,9 +411,11 @@ class Scheduler:
         budget = throttled_prefill_budget(headroom, self.world_size, self.mm.get_memory_free(), self.kvthresh,
                                           self.maxp, self.minp, self.iterp, len(self.seqs_to_prefill),
                                           self.num_wait_tokens)
-        prefill_batch, n_prefill = self.schedule_prefill_batch(budget)
         num_total_decode = self.get_num_decode_seqs()
         decode_budget = balanced_decode_budget(num_total_decode, self.pp_size, self.maxd)
+        room = None if self.max_seqs is None else \
+            max(self.max_seqs - min(decode_budget, len(self.seqs_to_decode)), 0)     # decode rows come first
+        prefill_batch, n_prefill = self.schedule_prefill_batch(budget, room)
         decode_batch = self.schedule_decode_batch(decode_budget)
         self._log_status(num_total_decode, n_prefill, len(decode_batch))
         return decode_batch + prefill_batch

@@ -523,3 +523,22 @@ def test_random_deepseek_v3_configs_match_hf():
             _check(m, page_size=rng.choice([8, 16]))
         except AssertionError as e:
             raise AssertionError(f"seed {seed}: {cfg.to_dict()}") from e
+
+
+def test_all_schedule_methods_generate_the_same_tokens():
+    """Greedy decoding does not depend on the batching policy. (token_throttling used to overflow the runner's
+    per-sequence buffers — capacity maxd — as soon as a full decode batch was joined by a prompt.)"""
+    import random
+    from gllm_b200 import LLM
+    from gllm_b200.models.presets import tiny
+    cfg = tiny("Qwen3ForCausalLM", num_hidden_layers=1)
+    rng = random.Random(3)
+    prompts = [[rng.randrange(5, 300) for _ in range(rng.randrange(1, 50))] for _ in range(16)]
+    outs = [rng.randrange(1, 20) for _ in prompts]
+    res = {}
+    for m in ("chunked_prefill", "split_pd", "token_throttling"):
+        llm = LLM(cfg, load_format="dummy", maxp=24, maxd=6, num_cpu_pages=64, page_size=4, log_stats=False,
+                  device="cpu", schedule_method=m, seed=0)
+        res[m] = [s.token_ids for s in llm.generate(tokens=prompts, output_lens=outs, ignore_eos=True)]
+        llm.shutdown()
+    assert res["split_pd"] == res["chunked_prefill"] and res["token_throttling"] == res["chunked_prefill"]

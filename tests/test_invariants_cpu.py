@@ -54,8 +54,9 @@ def test_random_streams_keep_kv_bookkeeping_consistent(seed, n_req, pages, metho
     PAGE = page       # small pages: preemption + prefix-cache hits + page-boundary cases every few tokens
     rng = random.Random(seed)
     mm = PrefixMemoryManager(pages, PAGE)
+    cap = 6 if method == "token_throttling" else maxp      # config.max_running_seqs of the engine
     sch = Scheduler(mm, pp_size=pp, world_size=pp, schedule_method=method, maxd=6, maxp=maxp, minp=4, iterp=2,
-                    kvthresh=kvthresh, page_size=PAGE, log=False)
+                    kvthresh=kvthresh, page_size=PAGE, log=False, max_seqs=cap)
     # prompts drawn from a few shared prefixes so that the prefix cache really gets hits and shared pages
     stems = [[rng.randrange(50) for _ in range(rng.randrange(2, 14))] for _ in range(3)]
     reqs = []
@@ -83,6 +84,7 @@ def test_random_streams_keep_kv_bookkeeping_consistent(seed, n_req, pages, metho
         check_invariants(mm, everyone)
         if batch:
             assert len(sch.batch_running) <= pp                              # <= pp micro-batches in flight
+            assert len(batch) <= cap                                         # fits the runner's per-sequence buffers
             n_dec = next((i for i, e in enumerate(batch) if not e.is_decode), len(batch))
             assert all(e.n == 1 and e.emits for e in batch[:n_dec])          # leading decode rows: one token each
             assert len({e.seq.seq_id for e in batch}) == len(batch)          # a sequence appears once per batch

@@ -32,7 +32,10 @@ def qwen3_8b_dir(path):
     with open(os.path.join(path, "config.json"), "w") as f:
         json.dump(cfg, f)
     with open(os.path.join(path, "generation_config.json"), "w") as f:
-        json.dump({"eos_token_id": [151645, 151643], "temperature": 0.6, "top_p": 0.95, "top_k": 20}, f)
+        # repetition_penalty: transformers 4 defaulted it to 1.0, transformers 5 leaves it None and the reference
+        # feeds generation_config.repetition_penalty straight into a float tensor (llm_engine.py:320-324)
+        json.dump({"eos_token_id": [151645, 151643], "temperature": 0.6, "top_p": 0.95, "top_k": 20,
+                   "repetition_penalty": 1.0}, f)
     tok = Tokenizer(models.WordLevel({f"t{i}": i for i in range(vocab)}, unk_token="t0"))
     tok.pre_tokenizer = pre_tokenizers.Whitespace()
     # model_max_length as in the real checkpoint's tokenizer_config.json: the reference derives its admission
@@ -47,7 +50,7 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--num-prompts", type=int, default=384)
+    ap.add_argument("--num-prompts", type=int, default=1000)
     ap.add_argument("--maxp", type=int, default=4096)
     ap.add_argument("--maxd", type=int, default=1024)
     ap.add_argument("--max-cuda-graph-bs", type=int, default=512)
@@ -71,24 +74,40 @@ def main():
         n_out = sum(len(s.token_ids) - s.prompt_len for s in seqs)
         return dt, n_out
 
+    # The reference's generate() has no ignore_eos switch: a sequence may stop early on an EOS id; the value counts
+    # the tokens it really produced (and `output_tokens_expected` says how many the workload asks for).
+    t_start = time.perf_counter()
+    budget = float(os.environ.get("GLLM_REF_BUDGET_S", "1e9"))
+    warm_done = 0
     for _ in range(args.warmup):
-        one_pass()
+        dt, _n = one_pass()
+        warm_done += 1
+        # keep room for at least one timed pass inside the caller's time limit
+        if time.perf_counter() - t_start + 2 * dt > budget:
+            break
     tot_t = tot_tok = 0
+    steps_done = 0
     for _ in range(args.steps):
         dt, n = one_pass()
         tot_t += dt
         tot_tok += n
+        steps_done += 1
+        if time.perf_counter() - t_start + dt > budget:
+            break
     value = tot_tok / tot_t
     print(json.dumps({
         "impl": "reference", "metric": "output_tokens_per_s", "value": round(value, 2), "unit": "tokens/s",
-        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": round(tot_t / args.steps * 1e3, 2), "higher_is_better": True, "scaling": "strong",
+        "n_gpus": args.gpus, "steps": steps_done, "warmup": warm_done,
+        "steps_requested": args.steps, "warmup_requested": args.warmup,
+        "ms_per_step": round(tot_t / steps_done * 1e3, 2),
+        "output_tokens_per_step": tot_tok // steps_done, "output_tokens_expected": sum(outs), "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "bf16",
         "data": "synthetic ShareGPT-shaped token ids (same generator and seed as our arm); random-init weights "
                 "(reference load_format=dummy)",
         "timing": "wall clock around LLM.generate in the front-end process (workers are separate processes)",
         "config": {"model": "Qwen3-8B", "num_prompts": args.num_prompts, "parallelism": f"tp{args.gpus}",
-                   "maxp": args.maxp, "maxd": args.maxd, "native_kernels": "vLLM 0.22 libraries of this image "
+                   "maxp": args.maxp, "maxd": args.maxd, "max_cuda_graph_bs": args.max_cuda_graph_bs,
+                   "enable_prefix_caching": True, "schedule_method": "chunked_prefill", "native_kernels": "vLLM 0.22 libraries of this image "
                    "(the reference pins vLLM 0.11)"},
         "e2e": {"value": round(value, 2), "unit": "tokens/s"}}), flush=True)
 

@@ -49,3 +49,45 @@ if _libs:
             torch.ops.load_library(_p)
         except Exception as _e:  # noqa: BLE001
             logger.warning("could not preload %s: %r", _p, _e)
+
+
+def _transformers5_config_glue():
+    """transformers 5 folds `rope_theta` / `rope_scaling` of a checkpoint's config.json into one `rope_parameters`
+    dict (`rope_scaling` becomes an alias of it, `rope_theta` disappears). The reference is written against
+    transformers 4 (`config.rope_theta`, `config.rope_scaling is None` for plain RoPE, models/qwen3.py:44-56):
+    give the loaded config objects back the transformers-4 attribute view. The reference itself is untouched."""
+    try:
+        import transformers
+    except Exception:  # noqa: BLE001
+        return
+    if getattr(transformers.AutoConfig, "_gllm_ref_glue", False):
+        return
+    orig = transformers.AutoConfig.from_pretrained.__func__
+
+    def _fix(cfg):
+        rp = getattr(cfg, "rope_parameters", None)
+        if isinstance(rp, dict) and "rope_type" in rp:
+            theta = rp.get("rope_theta")
+            rest = {k: v for k, v in rp.items() if k != "rope_theta"}
+            plain = rest.get("rope_type", "default") == "default" and "mrope_section" not in rest
+            try:
+                cfg.rope_scaling = None if plain else rest
+            except Exception:  # noqa: BLE001
+                pass
+            if plain:
+                cfg.__dict__["rope_parameters"] = None
+            if theta is not None:
+                cfg.__dict__["rope_theta"] = theta
+        for sub in ("text_config", "vision_config"):
+            if getattr(cfg, sub, None) is not None and sub in getattr(cfg, "__dict__", {}):
+                _fix(getattr(cfg, sub))
+        return cfg
+
+    def from_pretrained(cls, *a, **kw):
+        return _fix(orig(cls, *a, **kw))
+
+    transformers.AutoConfig.from_pretrained = classmethod(from_pretrained)
+    transformers.AutoConfig._gllm_ref_glue = True
+
+
+_transformers5_config_glue()

@@ -33,7 +33,8 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--model", default="preset:qwen3-8b")
-    ap.add_argument("--num-prompts", type=int, default=384)
+    ap.add_argument("--num-prompts", type=int, default=1000,
+                    help="the reference harness default (benchmarks/benchmark_throughput.py:359)")
     ap.add_argument("--maxp", type=int, default=4096)
     ap.add_argument("--maxd", type=int, default=1024)
     ap.add_argument("--max-cuda-graph-bs", type=int, default=512)
@@ -57,7 +58,7 @@ def reference_arm(args):
     ref_root = os.path.join(root, "baseline", "_ref")
 
     def unavailable(why):
-        print(json.dumps({"impl": "reference", "unavailable": " ".join(str(why).split())[:600]}))
+        print(json.dumps({"impl": "reference", "unavailable": " ".join(str(why).split())[:600]}), flush=True)
         return 0
 
     if not os.path.isfile(os.path.join(ref_root, "gllm", "llm_engine.py")):
@@ -82,7 +83,9 @@ def reference_arm(args):
            "--steps", str(args.steps), "--warmup", str(args.warmup), "--num-prompts", str(args.num_prompts),
            "--maxp", str(args.maxp), "--maxd", str(args.maxd), "--max-cuda-graph-bs", str(args.max_cuda_graph_bs),
            "--seed", str(args.seed)]
-    limit = int(os.environ.get("GLLM_REF_TIMEOUT", "1200"))
+    limit = int(os.environ.get("GLLM_REF_TIMEOUT", "1700"))
+    env.setdefault("GLLM_REF_BUDGET_S", str(limit - 240))   # run_reference.py stops timing new passes after this
+    env.setdefault("TQDM_DISABLE", "1")
     try:
         # own process group: on a timeout the reference's spawned workers are taken down with the front-end
         proc = subprocess.Popen(cmd, env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True,
@@ -107,7 +110,11 @@ def reference_arm(args):
         if line.startswith("{") and '"impl": "reference"' in line:
             print(line)
             return 0
-    tail = (err.strip().splitlines() or out.strip().splitlines() or ["no output"])[-1]
+    # the reference's front-end only `sys.exit()`s when a worker died: the worker's traceback is further up
+    lines = [ln for ln in (err + "\n" + out).replace("\r", "\n").splitlines() if ln.strip() and "it/s]" not in ln]
+    sys.stderr.write("---- reference arm failed; last 60 lines of its output ----\n" + "\n".join(lines[-60:]) + "\n")
+    errs = [ln for ln in lines if "Error" in ln or "error" in ln]
+    tail = (errs or lines or ["no output"])[-1]
     return unavailable(f"reference failed on this image (vLLM 0.22 / torch 2.11 / transformers 5 instead of its "
                        f"pinned 0.11 / 2.8 / <5): {tail}")
 
@@ -187,7 +194,7 @@ def main():
     tp = args.gpus // args.pp
     llm = LLM(args.model, load_format="dummy", tp_size=tp, pp_size=args.pp, maxp=args.maxp, maxd=args.maxd,
               max_cuda_graph_bs=args.max_cuda_graph_bs, schedule_method=args.schedule_method,
-              enable_prefix_caching=False, gpu_memory_util=0.85, model_max_length=2048 + 16,
+              enable_prefix_caching=True, gpu_memory_util=0.9, model_max_length=2048 + 16,
               tp_mode=args.tp_mode, log_stats=False, launch_mode="inproc", seed=args.seed,
               async_schedule=args.async_schedule)
     vocab = llm.loader.config["vocab_size"]
@@ -207,7 +214,9 @@ def main():
     for _ in range(args.warmup):
         one_pass()
 
-    # ---- region A: device-timed (CUDA events around the K steps), max over ranks ----
+    # ---- ONE timed region, two clocks: K passes through the public API (LLM.generate: every iteration copies its
+    # batch arrays host->device from pinned memory and reads the sampled tokens back), bracketed by barrier + sync.
+    # `value` = CUDA-event time on the launching stream, `e2e` = host wall clock around the same bracket.
     sampler = ClockSampler(int(os.environ.get("LOCAL_RANK", "0"))) if rank == 0 else None
     if sampler:
         sampler.start()
@@ -216,25 +225,20 @@ def main():
     stats0 = dict(runner.stats)
     launches0 = sm100.launches()
     barrier()
+    t0 = time.perf_counter()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
+    seqs = None
     for _ in range(args.steps):
-        one_pass()
+        seqs = one_pass()
     ev1.record()
     barrier()
+    wall_s = time.perf_counter() - t0
     dev_ms = ev0.elapsed_time(ev1)
     busy_ms = runner.gpu_busy_ms()
     runner.time_steps = False
     stats1 = dict(runner.stats)
     launches = (sm100.launches() - launches0) + (stats1["graph_kernel_launches"] - stats0["graph_kernel_launches"])
-    # ---- region B: end to end through the public API, wall clock ----
-    barrier()
-    t0 = time.perf_counter()
-    seqs = None
-    for _ in range(args.steps):
-        seqs = one_pass()
-    barrier()
-    wall_s = time.perf_counter() - t0
     if sampler:
         sampler.stop()
     if world > 1:
@@ -260,7 +264,7 @@ def main():
                           for q in seqs if q.first_token_time and q.finish_time and q.num_output_tokens > 1)
             lat = {"p50_ttft_ms": round(ttft[len(ttft) // 2], 1), "p99_ttft_ms": round(ttft[int(len(ttft) * 0.99)], 1),
                    "p50_tpot_ms": round(tpot[len(tpot) // 2], 2), "p99_tpot_ms": round(tpot[int(len(tpot) * 0.99)], 2),
-                   "arrival": "all requests at t0 (offline batch)"}
+                   "arrival": "all requests at t0 (offline batch)", "source": "last timed pass"}
         except Exception:  # noqa: BLE001
             pass
         out = {
@@ -289,12 +293,36 @@ def main():
             "latency": lat,
         }
         print(json.dumps(out), flush=True)
-    if world > 1 and dist.is_initialized():
-        dist.barrier()
     sys.stdout.flush()
     sys.stderr.flush()
-    # hard exit: tearing down NCCL / symmetric-memory handles in arbitrary order can stall at exit
-    os._exit(0)
+    teardown(llm, world)
+    return 0
+
+
+def teardown(llm, world):
+    """Orderly exit (no os._exit: exit-time hooks must run): quiesce the GPU, stop the engine, drop the symmetric
+    memory handles while every peer is still alive, then destroy the process group. A watchdog bounds a teardown
+    that stalls (it has not been seen to, but a hang here would hold the GPUs until the caller's timeout)."""
+    import torch
+    import torch.distributed as dist
+
+    def _bail():
+        sys.stderr.write("bench.py: teardown stalled for 120 s, forcing exit\n")
+        sys.stderr.flush()
+        os._exit(0)
+    dog = threading.Timer(120.0, _bail)
+    dog.daemon = True
+    dog.start()
+    torch.cuda.synchronize()
+    if world > 1 and dist.is_initialized():
+        dist.barrier()
+    try:
+        llm.close()
+    finally:
+        if world > 1 and dist.is_initialized():
+            dist.barrier()
+            dist.destroy_process_group()
+    dog.cancel()
 
 
 if __name__ == "__main__":

@@ -62,6 +62,7 @@ class AsyncStream:
         self.created = time.time()
         self.first_token_time: Optional[float] = None
         self.seq_id = -1
+        self.aborted = False     # an abort id was sent for this request (front-end side state only)
 
     def put(self, item: str):
         """Queue a text delta. With stop strings (OpenAI `stop`; not honoured by the reference) the text that could
@@ -154,12 +155,12 @@ class AsyncLLM(LLM):
         """Client went away: abort the request so its KV pages are freed (reference:
         async_llm_engine.py:93-97 polls `is_disconnected` from the engine task; here the request's own
         task reports it, which also works under ASGI test transports)."""
-        seq = self.running_maps.get(stream.seq_id)
-        if seq is None:      # accepted but not handed to the engine yet (the tick thread has not run `_send`)
-            seq = next((s for s in list(self.wait_lists) if s.seq_id == stream.seq_id), None)
-        if seq is not None and not seq.is_abort and not stream.finished:
+        # Only the abort id is sent: the Sequence object is shared with the in-proc scheduler, which must be the
+        # one to take it out of its queues before flagging it (a flag set from here while a prefill chunk was in
+        # flight left a freed sequence at the head of the prefill queue and took the engine down).
+        if not stream.aborted and not stream.finished:
+            stream.aborted = True
             self.abort([stream.seq_id])
-            seq.is_abort = True
             self.metrics["requests_aborted"] += 1
 
     async def collect(self, stream: AsyncStream) -> str:
@@ -203,9 +204,9 @@ class AsyncLLM(LLM):
             else:
                 st.put(" ".join(str(t) for t in seq.token_ids[seq.cur_length:seq.known_len]) + " ")
                 seq.cur_length = seq.known_len
-            if st.stop_hit and not seq.is_abort:      # a stop string completed: stop generating for this request
+            if st.stop_hit and not st.aborted:      # a stop string completed: stop generating for this request
+                st.aborted = True
                 self.abort([seq.seq_id])
-                seq.is_abort = True
         self._pending_tokens = []
         for seq in self.finished:
             st = self.async_streams.pop(seq.seq_id, None)
@@ -218,7 +219,11 @@ class AsyncLLM(LLM):
                 if st.first_token_time is not None and seq.num_output_tokens > 1:
                     self.hist["tpot"].observe((now - st.first_token_time) / (seq.num_output_tokens - 1))
                 reason = "length" if seq.num_output_tokens >= seq.output_len else "stop"
-                st.finish("abort" if seq.is_abort else reason)
+                if st.stop_hit:
+                    reason = "stop"
+                elif st.aborted or seq.is_abort:
+                    reason = "abort"
+                st.finish(reason)
         self.finished = []
 
     async def _loop(self):

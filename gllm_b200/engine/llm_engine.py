@@ -283,9 +283,10 @@ class LLM:
                 on_token(seq, tok)
         for sid in pkg.free_ids:
             seq = self.running_maps.pop(sid, None)
-            if seq is not None:
-                seq.finish_time = now
-                self.finished.append(seq)
+            if seq is None:
+                continue        # already released (a duplicate report must not free the id twice)
+            seq.finish_time = now
+            self.finished.append(seq)
             with self._inbox_lock:
                 self.id_allocator.free(sid)
         if pkg.stats:
@@ -432,6 +433,16 @@ class LLM:
         self.procs = []
         if comm is not None:
             comm.close(unlink_all=True)   # after the workers are gone: nobody is left to re-create the ipc files
+
+    def close(self):
+        """Full teardown for an orderly process exit: stop the workers, then release device-side state that other
+        ranks map (CUDA graphs first — they reference the peers' buffers —, then the symmetric-memory handles).
+        Collective when tp > 1: every rank calls it, peers still alive."""
+        worker = self.worker
+        self.shutdown()
+        runner = getattr(worker, "runner", None) if worker is not None else None
+        if runner is not None:
+            runner.close()
 
     def __del__(self):
         try:

@@ -57,8 +57,9 @@ class Worker(ProfilerMixin):
         self.frontend_out: Deque[IPCPackage] = deque()  # in-proc front-end mailbox
         self.frontend_in: Deque[IPCPackage] = deque()
         self.stop = False
-        self.slot_alloc = None
-        self._seq_slots = {}
+        self._seq_slots = {}                   # seq_id -> row of the penalty state it holds
+        self._free_slots = []                  # rows given back (row 0 = "no penalty state")
+        self._num_slots = 1
         self.init_profiler()
 
     # -------------------------------------------------------------------------------------------
@@ -81,7 +82,7 @@ class Worker(ProfilerMixin):
                                        minp=cfg.minp, iterp=cfg.iterp, kvthresh=cfg.kvthresh,
                                        page_size=cfg.page_size, log=cfg.log_stats,
                                        max_seqs=cfg.max_running_seqs)
-            self.slot_alloc = IDAllocator(1, max(cfg.max_running_seqs, 1))
+            self.scheduler.on_preempt = self._release_slot
         if self.mp_alive is not None:
             self.mp_alive[self.local_rank] = 1
         return self
@@ -102,11 +103,7 @@ class Worker(ProfilerMixin):
         for pkg in pkgs:
             if pkg.schedule_lists:
                 for seq in pkg.schedule_lists:
-                    if seq.repetition_penalty != 1.0 and seq.slot < 0:
-                        seq.slot = self.slot_alloc.allocate()
-                        self._seq_slots[seq.seq_id] = seq.slot
-                    elif seq.slot < 0:
-                        seq.slot = 0
+                    seq.slot = 0        # penalty state rows are assigned at the first emission (`_assign_slots`)
                 self.scheduler.add_new_requests(pkg.schedule_lists)
             if pkg.abort_ids:
                 self.scheduler.add_abort_ids(pkg.abort_ids)
@@ -173,9 +170,32 @@ class Worker(ProfilerMixin):
             self._launch(entries)
         return did
 
+    def _assign_slots(self, entries):
+        """Penalty state (the per-sequence seen-token bitmask on the device) is held only by sequences that are
+        sampling: a row is assigned when a sequence first emits and returned when it finishes, is aborted or is
+        preempted — never by waiting requests, whose number is unbounded. The pool grows on demand (the runner
+        grows the device tensor to match), so this cannot fail on the request path."""
+        for e in entries:
+            seq = e.seq
+            if e.emits and seq.repetition_penalty != 1.0 and seq.slot <= 0:
+                if self._free_slots:
+                    seq.slot = self._free_slots.pop()
+                else:
+                    seq.slot = self._num_slots
+                    self._num_slots += 1
+                seq.slot_fresh = True
+                self._seq_slots[seq.seq_id] = seq.slot
+
+    def _release_slot(self, seq):
+        slot = self._seq_slots.pop(seq.seq_id, 0)
+        if slot > 0:
+            self._free_slots.append(slot)
+        seq.slot = 0
+
     def _launch(self, entries):
         self.batch_counter += 1
         t0 = time.perf_counter()
+        self._assign_slots(entries)
         batch = build_batch(entries, self.cfg.page_size, self.runner.spec.vocab_size, self.batch_counter,
                             mrope=self.runner.input_data.mrope, prev=getattr(self, "_last_batch", None))
         if batch.feed_src is None and entries[0].seq.pending == entries[0].start:
@@ -200,7 +220,7 @@ class Worker(ProfilerMixin):
         for sid in out.free_ids:
             slot = self._seq_slots.pop(sid, 0)
             if slot > 0:
-                self.slot_alloc.free(slot)
+                self._free_slots.append(slot)
 
     # -------------------------------------------------------------------------------------------
     # peers

@@ -236,14 +236,16 @@ def build_batch(entries, page_size: int, vocab_size: int, batch_id: int = 0, mro
                 all_greedy = False
             if seq.repetition_penalty != 1.0:
                 need_penalty = True
-                if s0 < seq.prompt_len:
-                    # first emission of this sequence: its whole prompt becomes "seen"
+                if seq.slot_fresh:
+                    # the row was just (re)assigned — first emission, or first one after a preemption: everything
+                    # known so far (prompt and the tokens generated before) becomes "seen"
+                    seq.slot_fresh = False
                     clear_slots.append(seq.slot)
-                    seen_rows.append(np.full(seq.prompt_len, seq.slot, dtype=np.int32))
-                    seen_tokens.append(np.asarray(seq.token_ids[:seq.prompt_len], dtype=np.int32))
+                    seen_rows.append(np.full(s0 + e.n, seq.slot, dtype=np.int32))
+                    seen_tokens.append(np.asarray(seq.token_ids[:s0 + e.n], dtype=np.int32))
                 else:
-                    seen_rows.append(np.array([seq.slot], dtype=np.int32))
-                    seen_tokens.append(np.array([seq.token_ids[s0]], dtype=np.int32))
+                    seen_rows.append(np.full(e.n, seq.slot, dtype=np.int32))
+                    seen_tokens.append(np.asarray(seq.token_ids[s0:s0 + e.n], dtype=np.int32))
     mm = None
     if mrope:
         from gllm_b200.models.multimodal import batch_mm_payload

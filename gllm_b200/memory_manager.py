@@ -74,6 +74,11 @@ class MemoryManager:
         seq.pt_np = None
         seq.pt_gen += 1
         seq.page_hashes = []
+        seq.published = 0
+
+    def publish_computed(self, seq: Sequence):
+        """Hook called when a chunk of `seq` has returned (computed_token_num advanced); the prefix cache publishes
+        the pages that became complete."""
 
     def get_num_free_pages(self) -> int:
         return self.id_allocator.get_num_free_ids()
@@ -158,33 +163,24 @@ class PrefixMemoryManager(MemoryManager):
                 seq.scheduled_token_num += ps
                 self.num_hit_pages += 1
             seq.num_cached_tokens = seq.computed_token_num
+            seq.published = len(seq.page_table)
 
-    def pre_allocate_page(self, seqs: List[Sequence]):
+    def publish_computed(self, seq: Sequence):
+        """A page becomes a cache entry only once its KV has been written: called when a chunk returns, with
+        `computed_token_num` covering it. (Registering at allocation — as the reference does,
+        gllm/memory_manager.py:150-203 — lets an aborted / stall-broken / preempted sequence leave hashes behind
+        for pages it never filled; the next request with the same prefix would then attend to garbage.)"""
         ps = self.page_size
-        for seq in seqs:
-            # (hot loop of every decode step: attribute reads instead of the Sequence properties)
-            n_tok = len(seq.token_ids) - (1 if seq.pending >= 0 else 0)   # a trailing lookahead placeholder is
-            have = len(seq.page_table)                                    # not hashable yet (async scheduling)
-            if n_tok % ps != 0 and (seq.scheduled_token_num + ps - 1) // ps <= have:
-                continue    # 15 of 16 decode steps: no page completed, none needed
-            # a page completed by decode becomes cacheable
-            # (a chunked recompute after a preemption can get here with the page not allocated yet: then the
-            # allocation loop below registers its hash)
-            if seq.computed_prompt and n_tok % ps == 0 and 0 < n_tok // ps <= have:
-                self._extend_hashes(seq, n_tok // ps)
-                h = seq.page_hashes[n_tok // ps - 1]
-                page = seq.page_table[n_tok // ps - 1]
-                if h not in self.hash2page and self.page2hash[page] is None:
-                    self.page2hash[page] = h
-                    self.hash2page[h] = page
-            have = len(seq.page_table)
-            need = self.pages_needed(seq)
-            for i in range(have, have + need):
-                if (i + 1) * ps <= n_tok:
-                    self._extend_hashes(seq, i + 1)
-                    seq.page_table.append(self.allocate_page(seq.page_hashes[i]))
-                else:
-                    seq.page_table.append(self.allocate_page())
+        full = min(seq.computed_token_num // ps, len(seq.page_table))
+        if full <= seq.published:
+            return
+        self._extend_hashes(seq, full)
+        for i in range(seq.published, full):
+            h, page = seq.page_hashes[i], seq.page_table[i]
+            if h not in self.hash2page and self.page2hash[page] is None:
+                self.page2hash[page] = h
+                self.hash2page[h] = page
+        seq.published = full
 
     def get_cache_hit_rate(self) -> float:
         if self.num_allocated_pages == 0:

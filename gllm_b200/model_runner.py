@@ -297,7 +297,7 @@ class ModelRunner:
             logits = self.tpc.gather_logits(logits, self.spec.vocab_size)
         seen = None
         if batch.need_penalty:
-            seen = self._seen_bits()
+            seen = self._seen_bits(int(batch.state_slot.max()) + 1 if len(batch.state_slot) else 1)
             dev = self.device
             if batch.clear_slots is not None:
                 seen[torch.from_numpy(batch.clear_slots).to(dev).long()] = 0
@@ -361,11 +361,24 @@ class ModelRunner:
             res.tokens_host, res.event = self.tokens_host, ev
         return res
 
-    def _seen_bits(self):
-        if self.seen_bits is None:
+    def close(self):
+        if self.device is not None and torch.device(self.device).type == "cuda":
+            torch.cuda.synchronize()
+        self.graphs.clear()
+        tpc, self.tpc = self.tpc, None
+        if tpc is not None and hasattr(tpc, "close"):
+            tpc.close()
+
+    def _seen_bits(self, rows: int = 1):
+        """[rows, V/32] seen-token bitmask, one row per sequence holding penalty state (row 0: none). Grown (never
+        shrunk) to cover the largest row the driver has handed out: every rank sees the same `state_slot`."""
+        if self.seen_bits is None or self.seen_bits.shape[0] < rows:
             words = (self.spec.vocab_size + 31) // 32
-            self.seen_bits = torch.zeros(max(self.max_running_seqs, 1) + 1, words, dtype=torch.int32,
-                                         device=self.device)
+            n = max(rows, 65 if self.seen_bits is None else 2 * self.seen_bits.shape[0])
+            new = torch.zeros(n, words, dtype=torch.int32, device=self.device)
+            if self.seen_bits is not None:
+                new[: self.seen_bits.shape[0]] = self.seen_bits
+            self.seen_bits = new
         return self.seen_bits
 
 

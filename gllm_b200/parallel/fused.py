@@ -328,6 +328,15 @@ class FusedTPComm(TPComm):
         sm100._count()
         return self._reduce_norm(parity, self._rows_valid(), None, residual is not None, norm_w, eps)
 
+    def close(self):
+        """Drop the symmetric-memory mappings (collective: every rank of the group, peers alive)."""
+        torch.cuda.synchronize()
+        dist.barrier(group=self.group)
+        self.ep = None
+        self.cur_ag = None
+        self.hdl = None
+        self.blob = None
+
     # -------------------------------------------------------------------------------------------
     # expert-parallel all-to-all (csrc/comm/ep_a2a.cu)
     # -------------------------------------------------------------------------------------------

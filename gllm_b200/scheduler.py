@@ -109,6 +109,7 @@ class Scheduler:
         self.batch_running: Deque[List[ScheduledSeq]] = deque()
         self.next_tokens_queue: Deque[List[int]] = deque()
         self.abort_ids = set()
+        self.on_preempt = None      # callback(seq): the owner releases per-sequence device state
         self.num_preempt_seqs = 0
         self._log_preempt_at = 10
         self.num_wait_tokens = 0
@@ -175,15 +176,20 @@ class Scheduler:
                         self.mm.free(seq)
                 continue
             if seq.is_abort:
-                if seq.page_table:
-                    out.free_ids.append(seq.seq_id)
-                    if self._in_flight(seq):
-                        seq.zombie = True
-                    else:
-                        self.mm.free(seq)
+                # whoever flagged it (check_abort_seqs) took it out of the queues; be robust against a flag set
+                # elsewhere: a freed sequence left at the head of seqs_to_prefill would be scheduled again on an
+                # empty page table
+                self._drop_from_queues(seq)
+                self.mm.publish_computed(seq)
+                out.free_ids.append(seq.seq_id)     # exactly once: the zombie branch above never reports
+                if self._in_flight(seq):
+                    seq.zombie = True
+                else:
+                    self.mm.free(seq)
                 self.abort_ids.discard(seq.seq_id)
                 continue
             seq.computed_token_num = max(seq.computed_token_num, ent.start + ent.n)
+            self.mm.publish_computed(seq)
             if ent.emits:
                 tok = int(next_tokens[k - 1])
                 out.act_schedule_ids.append(seq.seq_id)
@@ -210,6 +216,13 @@ class Scheduler:
 
     def _in_flight(self, seq: Sequence) -> bool:
         return any(e.seq is seq for b in self.batch_running for e in b)
+
+    def _drop_from_queues(self, seq: Sequence):
+        for q in (self.seqs_to_prefill, self.seqs_to_decode):
+            try:
+                q.remove(seq)
+            except ValueError:
+                pass
 
     def schedule_lookahead(self) -> Optional[List["ScheduledSeq"]]:
         """Asynchronous scheduling: while the single in-flight decode batch is still running, schedule the decode
@@ -286,10 +299,15 @@ class Scheduler:
                     out.free_ids.append(seq.seq_id)
                     self.mm.free(seq)
                     self.abort_ids.discard(seq.seq_id)
+        live = set()
         for batch in self.batch_running:
             for ent in batch:
                 if ent.seq.seq_id in self.abort_ids:
                     ent.seq.is_abort = True
+                    live.add(ent.seq.seq_id)
+        # an abort that matches nothing alive (the sequence finished just before, or was never admitted) must not
+        # linger: it would disable lookahead scheduling for good and hit a later request that re-uses the id
+        self.abort_ids &= live
         return out if out.free_ids else None
 
     # -- scheduling -------------------------------------------------------------------------------
@@ -324,6 +342,8 @@ class Scheduler:
             if seq.page_table:
                 self.mm.free(seq)
                 seq.preempt()
+                if self.on_preempt is not None:
+                    self.on_preempt(seq)
                 self.num_preempt_seqs += 1
                 freed = True
                 if self.mm.get_num_free_pages() > self.num_kvthresh_pages:
@@ -336,6 +356,8 @@ class Scheduler:
             seq = self.seqs_to_decode.popleft()
             self.mm.free(seq)
             seq.preempt()
+            if self.on_preempt is not None:
+                self.on_preempt(seq)
             preempted.append(seq)
         if preempted:
             self.seqs_to_prefill.extendleft(preempted)

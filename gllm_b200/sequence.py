@@ -9,7 +9,8 @@ class Sequence:
                  "finish_tokens", "output_len", "cur_length", "temperature", "top_p", "top_k",
                  "repetition_penalty", "computed_token_num", "scheduled_token_num", "is_abort",
                  "mm_contents", "page_hashes", "num_cached_tokens", "arrival_time", "first_token_time",
-                 "finish_time", "slot", "mrope_delta", "mm_state", "pt_np", "pending", "zombie", "pt_gen")
+                 "finish_time", "slot", "mrope_delta", "mm_state", "pt_np", "pending", "zombie", "pt_gen", "published",
+                 "slot_fresh")
 
     def __init__(self, seq_id: int, token_ids: List[int], finish_tokens: List[int],
                  output_len: Optional[int] = None, ignore_eos: bool = False, temperature: float = 0.6,
@@ -40,6 +41,8 @@ class Sequence:
         self.arrival_time = 0.0
         self.first_token_time = 0.0
         self.finish_time = 0.0
+        self.published = 0   # leading pages of page_table already offered to the prefix cache
+        self.slot_fresh = False  # penalty state row just (re)assigned: rebuild its contents at the next emission
         self.slot = -1  # row in the persistent per-sequence device state (penalty bitmask, ...)
         self.mrope_delta = 0
         self.pt_np = None  # numpy mirror of page_table (rebuilt only when its length changes)
@@ -85,6 +88,7 @@ class Sequence:
         self.pt_np = None
         self.pt_gen += 1
         self.page_hashes = []
+        self.published = 0
         if self.mm_state:
             self.mm_state["sent"] = False  # the vision embeddings must be recomputed too
 

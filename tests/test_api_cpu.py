@@ -214,3 +214,44 @@ def test_disable_thinking_reaches_the_chat_template():
         llm.shutdown()
     extra = tok.encode("w1 w2", add_special_tokens=False)
     assert ids[False][-len(extra):] == extra and ids[True] == ids[False][:-len(extra)]
+
+
+def test_disconnect_mid_chunked_prefill_and_penalty_flood_do_not_kill_the_engine():
+    """ADVICE r1 (high + medium): (1) a client that goes away while its prompt is between two prefill chunks used to
+    leave a freed sequence at the head of the prefill queue -> double free of its id -> engine loop dead for good;
+    (2) more queued repetition-penalty requests than max_running_seqs exhausted the penalty-state pool on arrival."""
+    import asyncio
+    from gllm_b200.engine.async_llm_engine import AsyncLLM
+    d = _make_model_dir()
+    engine = AsyncLLM(d, maxp=16, maxd=16, num_cpu_pages=96, model_max_length=256, log_stats=False)
+
+    async def scenario():
+        prompt = [5 + (i * 7) % 190 for i in range(60)]
+        st = await engine.add_requests_async(None, prompt, output_len=8, ignore_eos=True, temperature=0.0, top_k=1)
+        for _ in range(2000):                      # let the first chunk(s) run, not the whole prompt
+            await asyncio.sleep(0.001)
+            seq = engine.running_maps.get(st.seq_id)
+            if seq is not None and 0 < seq.computed_token_num < 60:
+                break
+        engine.abort_stream(st)
+        engine.abort_stream(st)                    # idempotent
+        # the same prompt again plus a flood of penalty requests (24 > maxd = 16 = max_running_seqs)
+        streams = [await engine.add_requests_async(None, prompt, output_len=6, ignore_eos=True, temperature=0.0,
+                                                   top_k=1)]
+        for i in range(24):
+            streams.append(await engine.add_requests_async(None, [9 + i, 17, 23 + i, 31], output_len=5,
+                                                           ignore_eos=True, temperature=0.0, top_k=1,
+                                                           repetition_penalty=1.1))
+        texts = [await asyncio.wait_for(engine.collect(s), timeout=120) for s in streams]
+        return st, streams, texts
+
+    st, streams, texts = asyncio.run(scenario())
+    assert engine.failed is None
+    assert all(s.finish_reason == "length" for s in streams), [s.finish_reason for s in streams]
+    assert streams[0].completion_tokens == 6 and all(s.completion_tokens == 5 for s in streams[1:])
+    assert engine.metrics["requests_aborted"] == 1
+    sch = engine.worker.scheduler
+    assert not sch.abort_ids and not sch.has_work()
+    assert engine.worker.mm.get_num_free_pages() == engine.worker.mm.usable_pages      # nothing leaked
+    assert not engine.worker._seq_slots and not engine.running_maps
+    engine.shutdown()

@@ -83,6 +83,12 @@ def test_prefix_cache_hit_refcount_eviction():
     a.scheduled_token_num = 10
     mm.pre_allocate_page([a])
     assert len(a.page_table) == 3
+    # nothing is cacheable before the chunk has run: an identical prompt arriving now shares nothing
+    early = Sequence(9, list(range(10)), [2])
+    mm.pre_allocate_computed_page([early])
+    assert early.page_table == [] and early.computed_token_num == 0
+    a.computed_token_num = 10
+    mm.publish_computed(a)
     # identical prefix: two full pages are shared, refcount 2
     b = Sequence(2, list(range(10)), [2])
     mm.pre_allocate_computed_page([b])
@@ -127,9 +133,61 @@ def test_prefix_cache_decode_page_registered():
     a.append(8)  # -> 8 tokens: second page full
     a.scheduled_token_num = 8
     mm.pre_allocate_page([a])
+    a.computed_token_num = 8      # the decode steps that wrote tokens 6 and 7 have returned
+    mm.publish_computed(a)
     b = Sequence(2, [1, 2, 3, 4, 5, 6, 7, 8, 9], [2])
     mm.pre_allocate_computed_page([b])
     assert b.computed_token_num == 8
+
+
+def test_prefix_cache_never_serves_pages_that_were_not_computed():
+    """a sequence aborted (or stall-broken) between two prefill chunks left the hashes of pages it had only
+    allocated; a retry of the same prompt then skipped tokens whose KV was never written."""
+    ps = 16
+    mm = PrefixMemoryManager(64, ps, reserve_dummy_page=True)
+    sch = Scheduler(mm, maxp=40, maxd=8, page_size=ps, log=False, kvthresh=0.0)
+    prompt = [(7 * i) % 101 + 3 for i in range(100)]
+    a = Sequence(1, prompt, [2], output_len=4)
+    sch.add_new_requests([a])
+    batch = sch.schedule_once()
+    assert batch[0].n == 40 and not batch[0].emits
+    sch.add_next_tokens([])
+    sch.process_output()
+    assert a.computed_token_num == 40 and a.published == 2        # tokens 32..39 sit in a page that is not full
+    sch.add_abort_ids([1])
+    out = sch.check_abort_seqs()
+    assert out.free_ids == [1] and not sch.seqs_to_prefill
+    b = Sequence(2, prompt, [2], output_len=4)
+    sch.add_new_requests([b])
+    batch = sch.schedule_once()
+    assert batch[0].start == 32, batch      # only the two pages that were really written are reused
+
+
+def test_abort_between_prefill_chunks_reports_once_and_leaves_no_stale_id():
+    """(a) a sequence flagged while its chunk is in flight is freed and reported exactly once and never
+    scheduled again; (b) an abort id that matches nothing alive is dropped instead of lingering (it disabled
+    lookahead scheduling and hit the next request re-using the id)."""
+    ps = 16
+    mm = PrefixMemoryManager(64, ps, reserve_dummy_page=True)
+    sch = Scheduler(mm, maxp=16, maxd=8, page_size=ps, log=False, kvthresh=0.0)
+    a = Sequence(0, list(range(3, 63)), [2], output_len=4)
+    sch.add_new_requests([a])
+    assert sch.schedule_once()
+    a.is_abort = True                       # worst case: flagged from outside, still queued, chunk in flight
+    sch.add_abort_ids([0])
+    assert sch.check_abort_seqs() is None   # in flight: nothing to report yet
+    sch.add_next_tokens([])
+    out = sch.process_output()
+    assert out.free_ids == [0] and not a.page_table
+    assert not sch.seqs_to_prefill and not sch.has_work() and not sch.abort_ids
+    assert mm.get_num_free_pages() == 63
+    assert not sch.schedule_once()
+    sch.add_abort_ids([0, 77])              # late duplicates / unknown ids
+    assert sch.check_abort_seqs() is None and not sch.abort_ids
+    b = Sequence(0, list(range(3, 20)), [2], output_len=2)     # the id is re-used by a new request
+    sch.add_new_requests([b])
+    run_engine(sch)
+    assert b.num_output_tokens == 2 and not b.is_abort
 
 
 # ------------------------------------------------------------------------------------------------

@@ -85,7 +85,6 @@ def reference_arm(args):
            "--seed", str(args.seed)]
     limit = int(os.environ.get("GLLM_REF_TIMEOUT", "1700"))
     env.setdefault("GLLM_REF_BUDGET_S", str(limit - 240))   # run_reference.py stops timing new passes after this
-    env.setdefault("TQDM_DISABLE", "1")
     try:
         # own process group: on a timeout the reference's spawned workers are taken down with the front-end
         proc = subprocess.Popen(cmd, env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True,
@@ -284,6 +283,8 @@ def main():
                        "engine_iterations_per_step": eng_steps // max(args.steps, 1),
                        "cuda_graph_iterations": (stats1["graph_steps"] - stats0["graph_steps"]) // max(args.steps, 1),
                        "gpu_busy_fraction": round(busy_ms / dev_ms, 3),
+                       "device_ms_by_step_kind": {k: [v[0] // args.steps, round(v[1] / args.steps, 1), v[2] // args.steps]
+                                                  for k, v in sorted(getattr(runner, "busy_by_kind", {}).items())},
                        "total_tokens_per_s": round(args.steps * (total_in + total_out) / (dev_ms / 1e3), 1)},
             "clocks": sampler.summary() if sampler else None,
             "e2e": {"value": round(e2e, 1), "unit": "tokens/s",

@@ -252,13 +252,23 @@ class ModelRunner:
             if self.time_steps and self.device.type == "cuda":
                 ev1 = torch.cuda.Event(enable_timing=True)
                 ev1.record()
-                self._step_events.append((ev0, ev1))
+                kind = f"graph{bucket}" if bucket is not None else \
+                    ("decode_eager" if batch.is_decode_only() else "prefill")
+                self._step_events.append((ev0, ev1, kind, batch.num_tokens))
 
     def gpu_busy_ms(self) -> float:
         """Sum of per-step device time (CUDA events around forward + sampling); resets the log."""
         if self._step_events:
             self._step_events[-1][1].synchronize()
-        tot = sum(a.elapsed_time(b) for a, b in self._step_events)
+        tot = 0.0
+        self.busy_by_kind = {}        # kind -> [steps, device ms, tokens] of the log just consumed
+        for a, b, kind, ntok in self._step_events:
+            ms = a.elapsed_time(b)
+            tot += ms
+            acc = self.busy_by_kind.setdefault(kind, [0, 0.0, 0])
+            acc[0] += 1
+            acc[1] += ms
+            acc[2] += ntok
         self._step_events = []
         return tot
 

@@ -66,7 +66,14 @@ def main():
               schedule_method="chunked_prefill", master_port=str(int(os.environ.get("GLLM_REF_PORT", "18000"))),
               zmq_port_base=int(os.environ.get("GLLM_REF_PORT", "18000")) + 1)
 
+    n_pass = args.warmup + args.steps
+    pass_prompts = [prompts if i == 0 else synth_requests(args.num_prompts, 151936, args.seed, i)[0]
+                    for i in range(n_pass)]     # fresh token ids per pass, as in our arm (no cross-pass cache hits)
+    pass_no = [0]
+
     def one_pass():
+        prompts = pass_prompts[min(pass_no[0], n_pass - 1)]
+        pass_no[0] += 1
         t0 = time.perf_counter()
         # sampling arguments left at the reference's defaults: top_k defaults to 1, i.e. greedy (llm_engine.py:316-325)
         seqs = llm.generate(tokens=[list(p) for p in prompts], output_lens=list(outs))

@@ -29,7 +29,7 @@ class EngineConfig:
     use_ep: bool = True
     assigned_layers: Optional[List[int]] = None
     use_async_worker: bool = False
-    async_schedule: bool = False              # lookahead decode scheduling (next step queued before tokens return)
+    async_schedule: bool = True               # lookahead decode scheduling (next step queued before tokens return)
     use_thinking: bool = True
     schedule_method: str = "chunked_prefill"  # split_pd | chunked_prefill | token_throttling
     disable_cuda_graph: bool = False

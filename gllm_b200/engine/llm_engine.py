@@ -52,7 +52,7 @@ class LLM:
     def __init__(self, model_path, host=None, master_addr="127.0.0.1", master_port=8001, zmq_port_base=8002,
                  launch_mode="normal", worker_ranks=None, load_format="auto", gpu_memory_util=0.9, page_size=16,
                  maxd=2048, maxp=2048, minp=32, iterp=8, kvthresh=0.05, enable_prefix_caching=True, pp_size=1,
-                 tp_size=1, use_ep=True, assigned_layers=None, use_async_worker=False, async_schedule=False,
+                 tp_size=1, use_ep=True, assigned_layers=None, use_async_worker=False, async_schedule=True,
                  use_thinking=True,
                  schedule_method="chunked_prefill", disable_cuda_graph=False, max_cuda_graph_bs=32,
                  model_max_length=None, mm_processor_min_pixels=None, mm_processor_max_pixels=None, **extra):
@@ -326,7 +326,10 @@ class LLM:
             if not self.check_seq_length(toks, ol):
                 raise ValueError(f"request {i}: prompt ({len(toks)}) + output ({ol}) exceeds the model max length "
                                  f"{self.model_max_length}")
-            seqs.append(self.allocate_seq(toks, ol, ignore_eos, temperature, top_p, top_k, repetition_penalty,
+            def pick(v):            # sampling parameters: one value for all requests, or one per request
+                return v[i] if isinstance(v, (list, tuple)) else v
+            seqs.append(self.allocate_seq(toks, ol, ignore_eos, pick(temperature), pick(top_p), pick(top_k),
+                                          pick(repetition_penalty),
                                           mm_contents[i] if mm_contents is not None else None))
         self.add_requests(seqs)
         base = len(self.finished)

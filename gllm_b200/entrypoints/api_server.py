@@ -269,8 +269,9 @@ def make_parser() -> argparse.ArgumentParser:
     p.add_argument("--disable-thinking", action="store_true")
     p.add_argument("--model-max-length", type=int, default=None)
     p.add_argument("--use-async-worker", action="store_true")
-    p.add_argument("--async-schedule", action="store_true",
-                   help="queue the next decode step before the previous step's tokens are back on the host")
+    p.add_argument("--async-schedule", action=argparse.BooleanOptionalAction, default=True,
+                   help="queue the next decode step before the previous step's tokens are back on the host "
+                        "(default on; --no-async-schedule for the strictly synchronous loop)")
     p.add_argument("--gpu-memory-util", type=float, default=0.9)
     p.add_argument("--enable-prefix-caching", action="store_true")
     p.add_argument("--page-size", type=int, default=16)

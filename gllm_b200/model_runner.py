@@ -103,6 +103,8 @@ class ModelRunner:
         self.input_data.need_tok_seq = bool(self.loader.use_mla)
         # vocab-parallel sampling: the forward (and its CUDA graphs) ends at this rank's logits shard
         self.vp_sample = cfg.tp_size > 1 and os.environ.get("GLLM_VP_SAMPLE", "1") != "0"
+        # GLLM_VP_SAMPLE=greedy: vocab-parallel argmax only, sampled batches all-gather the logits (the round-1 path)
+        self.vp_candidates = os.environ.get("GLLM_VP_SAMPLE", "1") != "greedy"
         h, dt = self.spec.hidden_size, self.spec.dtype
         if not ps.is_first_pp_rank():
             self.input_hidden = torch.zeros(self.max_num_batched_tokens, h, dtype=dt, device=self.device)
@@ -301,10 +303,10 @@ class ModelRunner:
         e = logits.shape[0]
         if e == 0:
             return StepResult(tokens=self.tokens_out[:0], num_emit=0)
-        if self.vp_sample:
-            if batch.all_greedy and not batch.need_penalty:
-                return self._finish_sample(self._vp_greedy(logits), e)
-            logits = self.tpc.gather_logits(logits, self.spec.vocab_size)
+        if self.vp_sample and batch.all_greedy and not batch.need_penalty:
+            return self._finish_sample(self._vp_greedy(logits), e)
+        if self.vp_sample and not self.vp_candidates:
+            logits = self.tpc.gather_logits(logits, self.spec.vocab_size)   # GLLM_VP_SAMPLE=greedy: A/B switch
         seen = None
         if batch.need_penalty:
             seen = self._seen_bits(int(batch.state_slot.max()) + 1 if len(batch.state_slot) else 1)
@@ -324,8 +326,56 @@ class ModelRunner:
                         seen[rw, wd] |= bt
         if not batch.all_greedy:
             self.step_counter += 1
+        if self.vp_sample and self.vp_candidates:
+            return self._finish_sample(self._vp_sample(logits, seen), e)
         toks = Fn.sample(logits, inp, seen, seed=self.cfg.seed, step=self.step_counter)
         return self._finish_sample(toks, e)
+
+    VP_CANDIDATES = 256   # per rank and row; top_k <= this is exact (csrc/sample/sampler.cu)
+
+    def _vp_sample(self, shard: torch.Tensor, seen: Optional[torch.Tensor]) -> torch.Tensor:
+        """Vocab-parallel top-k / top-p / penalty sampling: every rank reduces its vocab shard to
+        a [E, 2C+4] record (C best candidates, softmax statistics, race winner), the ranks all-gather the records —
+        ~2 KB per row and rank instead of V/tp logits — and finish on the tp x C candidates with the exact global
+        normalisation. The [E, V] logits are never materialised (the reference all-gathers them and sorts the full
+        vocabulary: gllm/layers/vocab_parallel_embedding.py:423-435, gllm/layers/sampler.py:8-54)."""
+        import torch.distributed as dist
+        inp = self.input_data
+        e, per = shard.shape
+        st = ps.get_state()
+        r0 = st.tp_rank * per
+        v_full = self.spec.vocab_size
+        valid = max(0, min(per, v_full - r0))
+        c = min(self.VP_CANDIDATES, per)
+        pen = inp.rep_penalty[:e] if seen is not None else None
+        if shard.is_cuda:
+            from gllm_b200.ops import sm100
+            rec = sm100.vp_candidates(shard, valid, v_full, c, inp.temperature[:e], inp.top_k[:e], inp.top_p[:e],
+                                      pen, seen, inp.state_slot[:e] if seen is not None else None,
+                                      seed=self.cfg.seed, step=self.step_counter, vocab_offset=r0)
+        else:
+            from gllm_b200.ops import ref
+            step = int(self.step_counter) if self.step_counter is not None else 0
+            g = torch.Generator().manual_seed(self.cfg.seed + step)
+            race = torch.empty(e, per * st.tp_size).exponential_(1.0, generator=g)[:, r0:r0 + max(valid, 0)]
+            mask = None
+            if seen is not None:
+                rows = seen[inp.state_slot[:e].long()]
+                bits = (rows.unsqueeze(-1) >> torch.arange(32, dtype=torch.int32)) & 1
+                full = bits.reshape(e, -1).bool()
+                if full.shape[1] < r0 + valid:
+                    full = torch.nn.functional.pad(full, (0, r0 + valid - full.shape[1]))
+                mask = full[:, r0:r0 + valid]
+            rec = ref.vp_candidates(shard, valid, v_full, c, inp.temperature[:e], inp.top_k[:e], inp.top_p[:e], pen,
+                                    mask, race, vocab_offset=r0)
+        allr = torch.empty(st.tp_size, e, 2 * c + 4, dtype=torch.float32, device=shard.device)
+        dist.all_gather_into_tensor(allr.view(st.tp_size * e, 2 * c + 4), rec, group=st.tp_group)
+        self.stats["vp_sample_steps"] = self.stats.get("vp_sample_steps", 0) + 1
+        if shard.is_cuda:
+            return sm100.vp_final(allr, c, v_full, inp.top_k[:e], inp.top_p[:e], seed=self.cfg.seed,
+                                  step=self.step_counter)
+        g = torch.Generator().manual_seed(self.cfg.seed + step + 0x5bd1)
+        return ref.vp_final(allr, c, v_full, inp.top_k[:e], inp.top_p[:e], generator=g)
 
     def _vp_greedy(self, shard: torch.Tensor) -> torch.Tensor:
         """Vocab-parallel greedy sampling: every rank takes the argmax of its own vocab shard

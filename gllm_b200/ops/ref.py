@@ -279,6 +279,83 @@ def sample(logits: torch.Tensor, temperature=None, top_k=None, top_p=None, rep_p
     return tok.to(torch.int32)
 
 
+def vp_candidates(shard: torch.Tensor, valid: int, v_full: int, c: int, temperature=None, top_k=None, top_p=None,
+                  rep_penalty=None, seen_mask=None, race_exp: Optional[torch.Tensor] = None,
+                  vocab_offset: int = 0) -> torch.Tensor:
+    """PyTorch model of csrc/sample/sampler.cu:vp_candidates_kernel — per-row record [B, 2c+4]: the shard's c best
+    candidates after penalty / temperature (values, then token ids bit-cast to float), shard max, shard sum-exp, and
+    for unfiltered rows the shard's exponential-race winner (score relative to the shard max, token id).
+    `seen_mask` / `race_exp` are [B, valid] slices for this shard."""
+    b = shard.shape[0]
+    out = torch.full((b, 2 * c + 4), float("-inf"), dtype=torch.float32)
+    out[:, c:2 * c] = 0.0
+    out[:, 2 * c + 1] = 0.0
+    out[:, 2 * c + 3] = 0.0
+    if valid <= 0:
+        return out
+    x = apply_penalty_temperature(shard[:, :valid], temperature, rep_penalty, seen_mask)
+    m = x.max(dim=-1).values
+    out[:, 2 * c] = m
+    out[:, 2 * c + 1] = torch.exp(x - m.view(-1, 1)).sum(-1)
+    ck = min(c, valid)
+    vals, idx = torch.topk(x, ck, dim=-1)
+    out[:, :ck] = vals
+    out[:, c:c + ck] = (idx + vocab_offset).to(torch.int32).view(torch.float32)
+    k = top_k.long() if top_k is not None else torch.ones(b, dtype=torch.long)
+    k = torch.where((k <= 0) | (k > v_full), torch.full_like(k, v_full), k)
+    p = top_p.float() if top_p is not None else torch.ones(b)
+    free = (k >= v_full) & (p >= 1.0)
+    if bool(free.any()) and race_exp is not None:
+        score = (x - m.view(-1, 1)) - torch.log(race_exp[:, :valid])
+        best, bi = score.max(dim=-1)
+        out[free, 2 * c + 2] = best[free]
+        out[free, 2 * c + 3] = (bi[free] + vocab_offset).to(torch.int32).view(torch.float32)
+    return out
+
+
+def vp_final(gathered: torch.Tensor, c: int, v_full: int, top_k=None, top_p=None,
+             generator: Optional[torch.Generator] = None) -> torch.Tensor:
+    """PyTorch model of vp_final_kernel: finish top-k / top-p / draw on the gathered candidates [tp, B, 2c+4] with
+    the exact global normalisation (the mass of non-candidate tokens is known from the per-shard sum-exp)."""
+    tp, b, _ = gathered.shape
+    vals = gathered[:, :, :c].permute(1, 0, 2).reshape(b, tp * c)
+    toks = gathered[:, :, c:2 * c].contiguous().view(torch.int32).permute(1, 0, 2).reshape(b, tp * c).long()
+    ms, zs = gathered[:, :, 2 * c], gathered[:, :, 2 * c + 1]
+    gm = ms.max(dim=0).values
+    gz = (zs * torch.exp(torch.where(zs > 0, ms - gm.view(1, -1), torch.zeros_like(ms)))).sum(0)
+    n = tp * c
+    k = top_k.long() if top_k is not None else torch.ones(b, dtype=torch.long)
+    k = torch.where((k <= 0) | (k > v_full), torch.full_like(k, v_full), k)
+    p = top_p.float() if top_p is not None else torch.ones(b)
+    out = torch.zeros(b, dtype=torch.int32)
+    e_all = torch.empty(b, n).exponential_(1.0, generator=generator)
+    for r in range(b):
+        if k[r] >= v_full and p[r] >= 1.0:
+            sc = gathered[:, r, 2 * c + 2] + (ms[:, r] - gm[r])
+            out[r] = gathered[int(sc.argmax()), r, 2 * c + 3].view(torch.int32)
+            continue
+        x, t = vals[r], toks[r]
+        order = torch.argsort(x, descending=True, stable=True)
+        x, t = x[order], t[order]
+        kk = int(min(k[r], n))
+        if kk == 1:
+            out[r] = t[0]
+            continue
+        prob = torch.exp(x - gm[r])
+        keep = torch.zeros(n, dtype=torch.bool)
+        keep[:kk] = True
+        keep &= x >= x[kk - 1]
+        keep |= (x == x[kk - 1]) & (x > float("-inf"))      # ties at the threshold survive (as in the kernel)
+        mass = prob[keep].sum() if kk < v_full else gz[r]
+        if p[r] < 1.0:
+            cum = torch.cumsum(torch.where(keep, prob, torch.zeros_like(prob)), 0)
+            keep &= (cum - prob) < p[r] * mass
+        keep &= x > float("-inf")
+        score = torch.where(keep, torch.log(prob) - torch.log(e_all[r]), torch.full_like(prob, float("-inf")))
+        out[r] = t[int(score.argmax())]
+    return out
+
+
 # ----------------------------------------------------------------------------------------------
 # MoE
 # ----------------------------------------------------------------------------------------------

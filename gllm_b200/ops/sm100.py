@@ -225,10 +225,12 @@ def rope_kv_write(q: torch.Tensor, k: torch.Tensor, v: Optional[torch.Tensor], p
 # ----------------------------------------------------------------------------------------------
 _attn_ws = {}
 _FUSED_MERGE = os.environ.get("GLLM_ATTN_FUSED_MERGE", "0") == "1"
-# tcgen05 / TMEM prefill attention (csrc/attn/prefill_attention_tc.cu): opt-in until validated on hardware.
-# ATTN_TC_KV = keys per pipeline stage (64 or 128). Module attributes so tests / benches can flip them.
-ATTN_TC = os.environ.get("GLLM_ATTN_TC", "0") == "1"
-ATTN_TC_KV = int(os.environ.get("GLLM_ATTN_TC_KV", "128"))
+# tcgen05 / TMEM prefill attention (csrc/attn/prefill_attention_tc.cu) is the default prefill kernel (validated on
+# B200: profiles/attn_prefill_tc.md; 1.3-2.1x the mma.sync kernel); GLLM_ATTN_TC=0 selects the mma.sync kernel, which
+# also serves the shapes outside the tcgen05 kernel's envelope. ATTN_TC_KV = keys per pipeline stage (64 or 128;
+# 64 measured faster at every shape). Module attributes so tests / benches can flip them.
+ATTN_TC = os.environ.get("GLLM_ATTN_TC", "1") == "1"
+ATTN_TC_KV = int(os.environ.get("GLLM_ATTN_TC_KV", "64"))
 
 
 def decode_splits(num_seqs: int, num_kv_heads: int, num_q_heads: int, max_seq_len: int) -> int:
@@ -342,6 +344,41 @@ def sample(logits: torch.Tensor, temperature=None, top_k=None, top_p=None, rep_p
                        ctypes.c_uint64(seed & ((1 << 64) - 1)),
                        _p(step), _p(out_max), vocab_offset, stream_ptr())
     check(rc, "sample")
+    _count()
+    return out
+
+
+def vp_candidates(shard: torch.Tensor, valid: int, v_full: int, c: int, temperature=None, top_k=None, top_p=None,
+                  rep_penalty=None, seen_bits: Optional[torch.Tensor] = None,
+                  slot_idx: Optional[torch.Tensor] = None, seed: int = 0, step: Optional[torch.Tensor] = None,
+                  vocab_offset: int = 0) -> torch.Tensor:
+    """Vocab-parallel sampling, stage 1 (csrc/sample/sampler.cu): this rank's per-row record [B, 2c+4] fp32 — its c
+    best candidates (value, token id), (max, sum exp) of the shard, and the shard's race winner for unfiltered rows.
+    `valid`: columns of `shard` that are real vocabulary entries (the last rank's shard ends with padding)."""
+    assert shard.dim() == 2 and shard.stride(1) == 1 and shard.dtype in (_BF16, torch.float32)
+    b = shard.shape[0]
+    out = torch.empty(b, 2 * c + 4, dtype=torch.float32, device=shard.device)
+    seen_words = seen_bits.shape[1] if seen_bits is not None else 0
+    L = _lib.load()
+    rc = L.gllm_vp_candidates(_p(shard), 0 if shard.dtype == _BF16 else 1, shard.stride(0), _p(out), b, valid, v_full,
+                              c, _p(temperature), _p(top_k), _p(top_p), _p(rep_penalty), _p(seen_bits), seen_words,
+                              _p(slot_idx), ctypes.c_uint64(seed & ((1 << 64) - 1)), _p(step), vocab_offset,
+                              stream_ptr())
+    check(rc, "vp_candidates")
+    _count()
+    return out
+
+
+def vp_final(gathered: torch.Tensor, c: int, v_full: int, top_k=None, top_p=None, seed: int = 0,
+             step: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Vocab-parallel sampling, stage 2: `gathered` [tp, B, 2c+4] (all ranks' stage-1 records) -> tokens [B]."""
+    tp, b, w = gathered.shape
+    assert w == 2 * c + 4 and gathered.is_contiguous() and gathered.dtype == torch.float32
+    out = torch.empty(b, dtype=torch.int32, device=gathered.device)
+    L = _lib.load()
+    rc = L.gllm_vp_final(_p(gathered), tp, b, c, v_full, _p(top_k), _p(top_p),
+                         ctypes.c_uint64(seed & ((1 << 64) - 1)), _p(step), _p(out), stream_ptr())
+    check(rc, "vp_final")
     _count()
     return out
 

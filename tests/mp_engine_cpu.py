@@ -32,7 +32,23 @@ def main():
     from shard_util import load_global_weights
     load_global_weights(llm.worker.runner.model, cfg, seed=123)
     prompts = [[5, 17, 99, 200, 3, 45, 7], [9] * 40, list(range(20, 120)), [300, 301]]
-    outs = llm.generate(tokens=prompts, output_lens=[8] * 4, ignore_eos=True)
+    if os.environ.get("GLLM_TEST_SAMPLED") == "1":
+        # sampled + penalty requests next to greedy ones (vocab-parallel sampling under TP): rows 0 and 2 are greedy
+        # and must stay token-identical on every layout; rows 1 and 3 must come back complete and in vocabulary
+        seqs = llm.generate(tokens=prompts, output_lens=[8] * 4, ignore_eos=True, temperature=[0.0, 0.8, 0.0, 1.0],
+                            top_p=[1.0, 0.9, 1.0, 1.0], top_k=[1, 8, 1, 0], repetition_penalty=[1.0, 1.2, 1.3, 1.0])
+        outs = seqs
+        if int(os.environ.get("RANK", "0")) == 0:
+            vocab = cfg["vocab_size"]
+            assert all(len(s.token_ids) == len(p) + 8 and 0 <= min(s.token_ids) and max(s.token_ids) < vocab
+                       for s, p in zip(seqs, prompts)), [s.token_ids for s in seqs]
+            if tp > 1:
+                assert llm.worker.runner.stats.get("vp_sample_steps", 0) > 0, "vocab-parallel sampling did not run"
+            with open(out, "w") as f:
+                json.dump([seqs[0].token_ids, seqs[2].token_ids], f)
+        out = os.devnull
+    else:
+        outs = llm.generate(tokens=prompts, output_lens=[8] * 4, ignore_eos=True)
     if int(os.environ.get("RANK", "0")) == 0:
         with open(out, "w") as f:
             json.dump([s.token_ids for s in outs], f)

@@ -588,3 +588,53 @@ def test_incremental_detokenizer_streams_exactly_the_final_text():
         full = fast.decode(ids, skip_special_tokens=True)
         # text still held back (trailing partial character) is allowed to be missing, nothing else
         assert full == out or (full.startswith(out) and "\ufffd" in fast.decode(ids[-4:])), (trial, full, out)
+
+
+def test_vocab_parallel_sampling_model_matches_the_full_vocab_filter():
+    """per-shard candidates + (max, sum-exp) statistics are enough to finish top-k / top-p / penalty
+    sampling exactly — every draw lies in the support of the full-vocabulary filter, greedy rows give the argmax, and
+    the empirical distribution of a row matches the filtered distribution."""
+    import torch
+    from gllm_b200.ops import ref
+    torch.manual_seed(3)
+    tp, per, b, c = 4, 96, 6, 16
+    v_full = tp * per - 5                               # the last shard ends with padding columns
+    logits = torch.randn(b, tp * per) * 2.5
+    logits[:, v_full:] = 0.0
+    temperature = torch.tensor([0.7, 1.0, 1.3, 0.0, 0.9, 1.0])
+    top_k = torch.tensor([8, v_full, 3, 1, 16, v_full], dtype=torch.int32)
+    top_p = torch.tensor([0.9, 0.6, 1.0, 1.0, 0.5, 1.0])
+    pen = torch.tensor([1.0, 1.3, 1.0, 1.2, 1.0, 1.0])
+    seen = torch.rand(b, tp * per) < 0.3
+    probs = ref.sample_filter(logits[:, :v_full], temperature, top_k, top_p, pen, seen[:, :v_full])
+    hist = torch.zeros(b, v_full)
+    n_draw = 300
+    for it in range(n_draw):
+        g = torch.Generator().manual_seed(1000 + it)
+        race = torch.empty(b, tp * per).exponential_(1.0, generator=g)
+        recs = []
+        for r in range(tp):
+            lo = r * per
+            valid = max(0, min(per, v_full - lo))
+            recs.append(ref.vp_candidates(logits[:, lo:lo + per], valid, v_full, c, temperature, top_k, top_p, pen,
+                                          seen[:, lo:lo + valid], race[:, lo:lo + valid], vocab_offset=lo))
+        toks = ref.vp_final(torch.stack(recs), c, v_full, top_k, top_p, generator=g)
+        assert int(toks.min()) >= 0 and int(toks.max()) < v_full
+        hist[torch.arange(b), toks.long()] += 1
+    assert bool((probs[hist > 0] > 0).all()), "drew a token outside the filtered support"
+    x = ref.apply_penalty_temperature(logits[:, :v_full], temperature, pen, seen[:, :v_full])
+    assert int(hist[3].argmax()) == int(x[3].argmax()) and hist[3].max() == n_draw          # greedy row
+    for r in (0, 2, 4):                                                                       # small supports
+        emp = hist[r] / n_draw
+        assert float((emp - probs[r]).abs().max()) < 0.12, (r, emp[probs[r] > 0], probs[r][probs[r] > 0])
+    # unfiltered rows (pure temperature sampling over the whole vocabulary): the shard races reproduce a full-vocab
+    # Gumbel-max draw exactly
+    g = torch.Generator().manual_seed(7)
+    race = torch.empty(b, tp * per).exponential_(1.0, generator=g)
+    recs = [ref.vp_candidates(logits[:, r * per:(r + 1) * per], max(0, min(per, v_full - r * per)), v_full, c,
+                              temperature, top_k, top_p, pen, seen[:, r * per:r * per + max(0, min(per, v_full - r * per))],
+                              race[:, r * per:r * per + max(0, min(per, v_full - r * per))], vocab_offset=r * per)
+            for r in range(tp)]
+    toks = ref.vp_final(torch.stack(recs), c, v_full, top_k, top_p, generator=g)
+    full = (torch.log_softmax(x[5], -1) - torch.log(race[5, :v_full])).argmax()
+    assert int(toks[5]) == int(full)

@@ -122,3 +122,12 @@ def test_mixtral_tp2_without_expert_parallelism_matches_single(monkeypatch):
     ref_tokens = _run(1, 1, arch="MixtralForCausalLM")
     monkeypatch.setenv("GLLM_TEST_NO_EP", "1")
     assert _run(1, 2, arch="MixtralForCausalLM", port=29991) == ref_tokens
+
+
+def test_tp2_vocab_parallel_sampling_runs_and_keeps_greedy_rows_exact(monkeypatch):
+    """SURVEY §2.4 X4 under gloo: a batch mixing greedy, top-k/top-p + repetition-penalty and unfiltered temperature
+    rows never gathers the [E, V] logits at TP2 (the runner counts vocab-parallel sampling steps); its greedy rows
+    — one of them with a repetition penalty — reproduce the single-process tokens."""
+    monkeypatch.setenv("GLLM_TEST_SAMPLED", "1")
+    ref = _run(1, 1)
+    assert _run(1, 2, port=29901) == ref

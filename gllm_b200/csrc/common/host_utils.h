@@ -69,6 +69,28 @@ inline int make_tmap_2d(CUtensorMap* map, const void* base, uint64_t rows, uint6
   return 0;
 }
 
+// 3-D tensor [d2][d1][d0] (d0 contiguous) with byte strides for d1 and d2; box = [1][box_d1][box_d0], 128-byte
+// swizzle (box_d0 * elem_bytes == 128). Used for batched / strided operands (a [T, heads, K] activation read as
+// per-head [T, K] matrices without a transposing copy).
+inline int make_tmap_3d(CUtensorMap* map, const void* base, uint64_t d0, uint64_t d1, uint64_t d2,
+                        uint64_t stride1_bytes, uint64_t stride2_bytes, uint32_t box_d0, uint32_t box_d1,
+                        CUtensorMapDataType dtype) {
+  cuuint64_t dims[3] = {d0, d1, d2};
+  cuuint64_t strides[2] = {stride1_bytes, stride2_bytes};
+  cuuint32_t box[3] = {box_d0, box_d1, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = get_encode_fn()(map, dtype, 3, const_cast<void*>(base), dims, strides, box, estr,
+                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                               CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    fprintf(stderr, "[gllm_b200] cuTensorMapEncodeTiled(3d) failed (%d): base=%p dims=%llu,%llu,%llu strides=%llu,%llu\n",
+            (int)r, base, (unsigned long long)d0, (unsigned long long)d1, (unsigned long long)d2,
+            (unsigned long long)stride1_bytes, (unsigned long long)stride2_bytes);
+    return 1;
+  }
+  return 0;
+}
+
 // Programmatic dependent launch: the kernel may start (prologue, weight prefetch) while its predecessor in the
 // stream is still draining; it must execute `griddep_wait()` (ptx.cuh) before touching anything the
 // predecessor wrote. Only kernels written that way are launched through this helper. GLLM_PDL=0 disables it.

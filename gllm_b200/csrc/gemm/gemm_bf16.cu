@@ -54,6 +54,12 @@ struct GemmParams {
   // per-row destination table (EP combine push): row r of C is stored at row_dest[r] (any rank's memory
   // mapped over NVLink); 0 = padding row, not stored. comm/ep_a2a.cu builds the table.
   const int64_t* row_dest;
+  // batched mode (batch > 0): `batch` independent [rows_per_batch, K] x [N, K]^T products over strided operands —
+  // A is a 3-D tensor map (k, row, batch), batch b uses the weight slab b ([batch, N, K] contiguous) and writes
+  // C + row * ldc + b * c_batch_stride. MLA weight absorption (q_nope·W_UK, out_lat·W_UV per head) runs on it
+  // instead of a cuBLAS bmm (reference: gllm/layers/attention.py:463-484).
+  int batch, rows_per_batch;
+  int64_t c_batch_stride;
   // split-K (decode-sized M): unit = (tile, k-slice); partials go through an fp32 workspace in a
   // thread-private layout, the last-arriving CTA of a tile sums them in slice order and runs the epilogue
   int split_k;
@@ -99,11 +105,13 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   // while the previous kernel drains. Grouped (MoE) mode reads device-side tile metadata right away, so it
   // waits here; the dense path first puts weight tiles in flight (producer warp below) and waits afterwards.
   griddep_launch();
-  const bool grouped = p.tile_expert != nullptr || p.num_m_tiles_ptr != nullptr;
+  const bool grouped = p.tile_expert != nullptr || p.num_m_tiles_ptr != nullptr || p.batch > 0;
   if (grouped) griddep_wait();
 
-  const int num_m = p.num_m_tiles_ptr != nullptr ? min(*p.num_m_tiles_ptr, (p.M + kBlockM - 1) / kBlockM)
-                                                 : (p.M + kBlockM - 1) / kBlockM;
+  const int tpb = p.batch > 0 ? (p.rows_per_batch + kBlockM - 1) / kBlockM : 0;   // M tiles per batch entry
+  const int num_m = p.batch > 0 ? p.batch * tpb
+                    : p.num_m_tiles_ptr != nullptr ? min(*p.num_m_tiles_ptr, (p.M + kBlockM - 1) / kBlockM)
+                                                   : (p.M + kBlockM - 1) / kBlockM;
   const int num_n = (p.N + BN - 1) / BN;
   const int num_tiles = num_m * num_n;
   const int num_kb = (p.K + kBlockK - 1) / kBlockK;
@@ -162,7 +170,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         const int mt = ((tile % num_m) + p.m_rot) % num_m;
         const int m0 = mt * kBlockM;
         const int n0 = (tile / num_m) * BN;
-        const int b_row_off = p.tile_expert != nullptr ? p.tile_expert[mt] * p.n_per_expert : 0;
+        const int bidx = p.batch > 0 ? mt / tpb : 0;
+        const int b_row_off = p.batch > 0 ? bidx * p.n_per_expert
+                              : p.tile_expert != nullptr ? p.tile_expert[mt] * p.n_per_expert : 0;
         if (p.a_ready != nullptr) {
           // all-gather ⊕ GEMM: the 128-row block `mt` of A is complete once its arrival counter reached
           // the device-resident expected value (advanced by rs_reduce_norm, comm/tp_fused.cu)
@@ -182,7 +192,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           }
           mbar_wait(&empty_bar[s], ph ^ 1);
           mbar_expect_tx(&full_bar[s], Cfg::kStageBytes);
-          tma_load_2d(sa, &tmap_a, &full_bar[s], kb * kBlockK, m0, kEvictNormal);
+          if (p.batch > 0) tma_load_3d(sa, &tmap_a, &full_bar[s], kb * kBlockK, (mt - bidx * tpb) * kBlockM, bidx);
+          else tma_load_2d(sa, &tmap_a, &full_bar[s], kb * kBlockK, m0, kEvictNormal);
           tma_load_2d(sb, &tmap_b, &full_bar[s], kb * kBlockK, n0 + b_row_off, kEvictNormal);
         }
       }
@@ -234,8 +245,15 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       const uint32_t aph = (tcount >> 1) & 1;
       mbar_wait(&tmem_full[buf], aph);
       tc_fence_after();
-      const int row = m0 + q * 32 + lane;
-      const bool row_in = row < p.M;
+      int row = m0 + q * 32 + lane;
+      bool row_in = row < p.M;
+      int64_t c_off = 0;
+      if (p.batch > 0) {   // tile -> (batch entry, row inside it)
+        const int mt = m0 / kBlockM, bidx = mt / tpb;
+        row = (mt - bidx * tpb) * kBlockM + q * 32 + lane;
+        row_in = row < p.rows_per_batch;
+        c_off = static_cast<int64_t>(bidx) * p.c_batch_stride;
+      }
       const uint32_t t_row = tmem_base + buf * BN + (static_cast<uint32_t>(q * 32) << 16);
 
       // destination row pointer (local C, or the owner rank's staging buffer for RS)
@@ -253,7 +271,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           crow = p.peer_out[owner] +
                  (static_cast<size_t>(p.rs_rank) * p.rows_per_rank + r_local) * p.ldc;
         } else {
-          crow = p.C + static_cast<size_t>(row) * p.ldc;
+          crow = p.C + static_cast<size_t>(row) * p.ldc + c_off;
         }
       }
 
@@ -652,6 +670,33 @@ GLLM_EXPORT int gllm_gemm_bf16_tiles_covering(int M, int N, int K, int epi, int 
   const int t0 = row0 / kBlockM;
   const int t1 = (row1 - 1) / kBlockM;
   return (t1 - t0 + 1) * ((N + bn - 1) / bn) * split;  // every k-slice unit publishes its column share
+}
+
+// Batched GEMM over strided operands: for b in [0, B): C[:, b, :] = A[:, b, :] · W[b]^T with A [T, B, K] (row stride
+// lda_t, batch stride lda_b, elements), W [B, N, K] contiguous, C [T, B, N] (row stride ldc_t, batch stride ldc_b).
+GLLM_EXPORT int gllm_gemm_bf16_batched(const void* A, int64_t lda_t, int64_t lda_b, const void* W, void* C,
+                                       int64_t ldc_t, int64_t ldc_b, int T, int B, int N, int K, void* stream) {
+  if (T <= 0 || B <= 0) return 0;
+  if ((K % 8) != 0 || (N % 8) != 0 || (lda_t % 8) != 0 || (lda_b % 8) != 0 || (ldc_t % 8) != 0 || (ldc_b % 8) != 0) {
+    fprintf(stderr, "[gllm_b200] gemm_bf16_batched: K, N and strides must be multiples of 8\n");
+    return 1;
+  }
+  const int bn = 128;
+  CUtensorMap ta, tb;
+  if (make_tmap_3d(&ta, A, K, T, B, lda_t * 2, lda_b * 2, kBlockK, kBlockM, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16)) return 1;
+  if (make_tmap_2d(&tb, W, static_cast<uint64_t>(B) * N, K, static_cast<uint64_t>(K) * 2, bn, kBlockK,
+                   CU_TENSOR_MAP_DATA_TYPE_BFLOAT16)) return 1;
+  GemmParams p;
+  memset(&p, 0, sizeof(p));
+  const int tpb = (T + kBlockM - 1) / kBlockM;
+  p.M = B * tpb * kBlockM; p.N = N; p.K = K;
+  p.C = reinterpret_cast<__nv_bfloat16*>(C);
+  p.ldc = static_cast<int>(ldc_t);
+  p.batch = B;
+  p.rows_per_batch = T;
+  p.c_batch_stride = ldc_b;
+  p.n_per_expert = N;
+  return launch_gemm<128, kEpiStore>(ta, tb, p, reinterpret_cast<cudaStream_t>(stream));
 }
 
 // Grouped (MoE) GEMM: rows of A are expert-sorted and padded to 128-row tiles; tile t uses the weight

@@ -182,7 +182,7 @@ class SparseMoeBlock(nn.Module):
         self.shared = None
         self.shared_gate_w = None
         if m.shared_intermediate_size > 0:
-            self.shared = DenseMLP(spec.hidden_size, m.shared_intermediate_size, spec.dtype, device)
+            self.shared = DenseMLP(spec.hidden_size, m.shared_intermediate_size, spec.dtype, device, spec=spec)
             if m.shared_gate:
                 self.shared_gate_w = _param(1, spec.hidden_size, dtype=spec.dtype, device=device)
 
@@ -191,7 +191,7 @@ class SparseMoeBlock(nn.Module):
         if self.shared is not None:
             # partial (un-reduced) shared-expert output: reduced together with the routed experts —
             # the reference double-reduces here on Qwen2-MoE; we do it once.
-            s = Fn.linear(self.shared.act(h, tpc), self.shared.down_w)
+            s = Fn.linear(self.shared.act(h, tpc), self.shared.down_weight())
             if self.shared_gate_w is not None:
                 g = torch.sigmoid(torch.nn.functional.linear(h.float(), self.shared_gate_w.float()))
                 s = (s.float() * g).to(s.dtype)
@@ -231,7 +231,9 @@ class SparseMoeBlock(nn.Module):
             tp, tr = ex.tp_size, ex.tp_rank
             gate, up = reader.get(sp + "gate_proj.weight"), reader.get(sp + "up_proj.weight")
             self.shared.set_gate_up(wu.shard_gate_up(gate, up, tr, tp))
-            self.shared.down_w.data.copy_(wu.shard_cols(reader.get(sp + "down_proj.weight"), tr, tp))
+            from gllm_b200.models.decoder import _store_linear
+            _store_linear(self.shared.down_w, self.shared.down_ws,
+                          wu.shard_cols(reader.get(sp + "down_proj.weight"), tr, tp))
             if self.shared_gate_w is not None:
                 self.shared_gate_w.data.copy_(reader.get(pre + nm["shared_gate"]))
 

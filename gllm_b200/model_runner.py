@@ -102,6 +102,9 @@ class ModelRunner:
                                     self.device, mrope=mrope)
         self.input_data.need_tok_seq = bool(self.loader.use_mla)
         # vocab-parallel sampling: the forward (and its CUDA graphs) ends at this rank's logits shard
+        # test hook (tests/mp_tp_check.py): keep the full last-token logits of every step, per emitting sequence id
+        self.keep_logits = os.environ.get("GLLM_KEEP_LOGITS", "0") == "1"
+        self.logit_log = []
         self.vp_sample = cfg.tp_size > 1 and os.environ.get("GLLM_VP_SAMPLE", "1") != "0"
         # GLLM_VP_SAMPLE=greedy: vocab-parallel argmax only, sampled batches all-gather the logits (the round-1 path)
         self.vp_candidates = os.environ.get("GLLM_VP_SAMPLE", "1") != "greedy"
@@ -303,6 +306,9 @@ class ModelRunner:
         e = logits.shape[0]
         if e == 0:
             return StepResult(tokens=self.tokens_out[:0], num_emit=0)
+        if self.keep_logits:
+            full = self.tpc.gather_logits(logits, self.spec.vocab_size) if self.vp_sample else logits
+            self.logit_log.append((list(batch.emit_ids or []), full[:e, : self.spec.vocab_size].float().cpu()))
         if self.vp_sample and batch.all_greedy and not batch.need_penalty:
             return self._finish_sample(self._vp_greedy(logits), e)
         if self.vp_sample and not self.vp_candidates:

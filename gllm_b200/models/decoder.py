@@ -109,7 +109,7 @@ def _param(*shape, dtype, device, std=0.02, fill=None):
 
 def _linear_params(n: int, k: int, spec: ModelSpec, device):
     """(weight, scale_inv | None): bf16 [n, k], or e4m3 [n, k] + fp32 block scales for fp8 checkpoints."""
-    if spec.quant == "fp8":
+    if spec.quant == "fp8" and k % 128 == 0:      # activations are quantised per 128-wide K group
         w = nn.Parameter(torch.zeros(n, k, dtype=torch.float8_e4m3fn, device=device), requires_grad=False)
         s = nn.Parameter(torch.ones((n + 127) // 128, (k + 127) // 128, dtype=torch.float32, device=device),
                          requires_grad=False)

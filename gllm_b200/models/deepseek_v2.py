@@ -7,11 +7,12 @@ gllm/memory_manager.py:38-42) — and q heads are split over TP. Routing uses th
 kernel (sigmoid + bias-corrected `noaux_tc` for V3), experts run through the grouped tcgen05 GEMMs,
 shared experts are an ordinary gated MLP whose partial output is reduced together with the routed one.
 
-Round-1 status of the attention math: correct for prefill, chunked prefill, prefix hits and decode on
-CPU and GPU, but evaluated in the *expanded* form with PyTorch ops per sequence (latent rows of the
-sequence are gathered from the paged cache and up-projected through kv_b_proj). The absorbed
-(q·W_UK / W_UV) split-KV sm_100a kernel over the 576-wide latent is the planned replacement
-(SURVEY §2.3 K11/K13); until then MLA models are functional but not on the fast path.
+On sm_100a the attention runs in the *absorbed* form: q_nope·W_UK per head (batched tcgen05 GEMM over strided
+views, written straight into the 576-wide query), fused RoPE + latent-cache write, split-KV multi-query attention
+over the paged latent cache (csrc/attn/mla_attention.cu), then out_lat·W_UV per head (the same batched GEMM,
+written in the [T, heads·v] layout o_proj reads). No cuBLAS and no host synchronisation on that path, so decode
+batches run inside CUDA graphs. The CPU / odd-shape path below evaluates the *expanded* form
+with PyTorch ops per sequence (the numerical oracle of the GPU path).
 """
 from __future__ import annotations
 
@@ -25,7 +26,8 @@ from gllm_b200.layers import functional as Fn
 from gllm_b200.layers.moe import SparseMoeBlock
 from gllm_b200.layers.rotary import build_rope
 from gllm_b200.models import weight_utils as wu
-from gllm_b200.models.decoder import CausalLM, DenseMLP, ModelSpec, MoESpec, _param
+from gllm_b200.models.decoder import (CausalLM, DenseMLP, ModelSpec, MoESpec, _linear_params, _param, _qw,
+                                      _store_linear)
 from gllm_b200.models.registry import _dtype
 from gllm_b200.ops import ref
 from gllm_b200.parallel import state as ps
@@ -48,16 +50,19 @@ class MLAAttention(nn.Module):
         self.eps = spec.rms_eps
         self.scaling = self.qk_dim ** -0.5 * rope.attn_mscale
         h, dt = spec.hidden_size, spec.dtype
+        # The projections follow the checkpoint's quantisation (fp8 block-scaled for V3 / R1: (weight, scale_inv)
+        # pairs on the UTCQMMA GEMM — reference plumbs quant_config into them, gllm/models/deepseek_v2.py:280-440).
+        # kv_b_proj stays bf16: it is only ever used absorbed, as the per-head W_UK / W_UV operands.
         if self.q_lora:
-            self.q_a_w = _param(self.q_lora, h, dtype=dt, device=device)
+            self.q_a_w, self.q_a_ws = _linear_params(self.q_lora, h, spec, device)
             self.q_a_norm_w = _param(self.q_lora, dtype=dt, device=device, fill=1.0)
-            self.q_b_w = _param(self.num_heads * self.qk_dim, self.q_lora, dtype=dt, device=device)
+            self.q_b_w, self.q_b_ws = _linear_params(self.num_heads * self.qk_dim, self.q_lora, spec, device)
         else:
-            self.q_w = _param(self.num_heads * self.qk_dim, h, dtype=dt, device=device)
-        self.kv_a_w = _param(self.kv_lora + self.rope_dim, h, dtype=dt, device=device)
+            self.q_w, self.q_ws = _linear_params(self.num_heads * self.qk_dim, h, spec, device)
+        self.kv_a_w, self.kv_a_ws = _linear_params(self.kv_lora + self.rope_dim, h, spec, device)
         self.kv_a_norm_w = _param(self.kv_lora, dtype=dt, device=device, fill=1.0)
         self.kv_b_w = _param(self.num_heads * (self.nope + self.v_dim), self.kv_lora, dtype=dt, device=device)
-        self.o_w = _param(h, self.num_heads * self.v_dim, dtype=dt, device=device)
+        self.o_w, self.o_ws = _linear_params(h, self.num_heads * self.v_dim, spec, device)
         self.o_b = None
         # attributes the generic runner looks at
         self.num_kv_heads = 1
@@ -68,12 +73,12 @@ class MLAAttention(nn.Module):
         hl = self.num_heads
         h = tpc.materialize(h)
         if self.q_lora:
-            qa, _ = Fn.rmsnorm(Fn.linear(h, self.q_a_w), self.q_a_norm_w, self.eps)
-            q = Fn.linear(qa, self.q_b_w)
+            qa, _ = Fn.rmsnorm(Fn.linear(h, _qw(self.q_a_w, self.q_a_ws)), self.q_a_norm_w, self.eps)
+            q = Fn.linear(qa, _qw(self.q_b_w, self.q_b_ws))
         else:
-            q = Fn.linear(h, self.q_w)
+            q = Fn.linear(h, _qw(self.q_w, self.q_ws))
         q = q.view(t, hl, self.qk_dim)
-        kv_a = Fn.linear(h, self.kv_a_w)
+        kv_a = Fn.linear(h, _qw(self.kv_a_w, self.kv_a_ws))
         kv_c, _ = Fn.rmsnorm(kv_a[:, : self.kv_lora].contiguous(), self.kv_a_norm_w, self.eps)
         if kv_cache is None:
             return q[:, :, : self.v_dim].reshape(t, hl * self.v_dim).contiguous()
@@ -115,14 +120,16 @@ class MLAAttention(nn.Module):
         if not self.kv_b_w.is_cuda:
             return
         kvb = self.kv_b_w.data.view(self.num_heads, self.nope + self.v_dim, self.kv_lora)
-        w_uk, w_uv = kvb[:, : self.nope, :], kvb[:, self.nope:, :].transpose(1, 2)
+        # both in the [batch, N, K] (nn.Linear) layout the batched GEMM reads:
+        #   q_lat[:, h] = q_nope[:, h] @ W_UK[h]      -> weight [512 (N), nope (K)] = W_UK[h]^T
+        #   out[:, h]   = out_lat[:, h] @ W_UV[h]^T   -> weight [v (N), 512 (K)]    = kv_b rows of the value part
+        w_uk_nk, w_uv_nk = kvb[:, : self.nope, :].transpose(1, 2), kvb[:, self.nope:, :]
         old = getattr(self, "_w_abs", None)
         if old is not None:   # keep the addresses: captured CUDA graphs point at these tensors
-            old[0].copy_(w_uk)
-            old[1].copy_(w_uv)
+            old[0].copy_(w_uk_nk)
+            old[1].copy_(w_uv_nk)
         else:
-            self._w_abs = (w_uk.contiguous(),    # q_lat = q_nope @ W_UK
-                           w_uv.contiguous())    # out   = out_lat @ W_UV
+            self._w_abs = (w_uk_nk.contiguous(), w_uv_nk.contiguous())
 
     def _absorbed_weights(self):
         if getattr(self, "_w_abs", None) is None:
@@ -137,15 +144,15 @@ class MLAAttention(nn.Module):
         t, hl = q.shape[0], self.num_heads
         w_uk, w_uv = self._absorbed_weights()
         q_full = torch.empty(t, hl, 576, dtype=q.dtype, device=q.device)
-        q_lat = torch.bmm(q[:, :, : self.nope].transpose(0, 1), w_uk)        # [hl, T, 512]
-        q_full[:, :, :512].copy_(q_lat.transpose(0, 1))
+        sm100.gemm_batched(q[:, :, : self.nope], w_uk, q_full[:, :, :512])   # per head: q_nope · W_UK
         sm100.mla_rope_cache(q[:, :, self.nope:], q_full, k_pe, kv_c, self.rope.cos_sin, inp.positions,
                              inp.slot_mapping, cache)
         splits = sm100.mla_splits(t, hl)
         out_lat = sm100.mla_attention(q_full, cache, inp.block_table, inp.tok_seq, inp.positions, self.scaling,
                                       splits=splits)
-        out = torch.bmm(out_lat.transpose(0, 1), w_uv)                        # [hl, T, v]
-        return out.transpose(0, 1).reshape(t, hl * self.v_dim)
+        out = torch.empty(t, hl, self.v_dim, dtype=q.dtype, device=q.device)
+        sm100.gemm_batched(out_lat, w_uv, out)                                # per head: out_lat · W_UV
+        return out.view(t, hl * self.v_dim)
 
 
 class DeepseekDecoderLayer(nn.Module):
@@ -158,12 +165,12 @@ class DeepseekDecoderLayer(nn.Module):
         self.attn = MLAAttention(spec, local_id, rope, device)
         self.is_moe = spec.is_moe_layer(layer_id)
         self.mlp = SparseMoeBlock(spec, layer_id, device) if self.is_moe else \
-            DenseMLP(h, spec.intermediate_size, dt, device)
+            DenseMLP(h, spec.intermediate_size, dt, device, spec=spec)
 
     def forward(self, inp, h, residual, kv_cache, tpc: TPComm, next_norm_w):
         eps = self.spec.rms_eps
         a = self.attn(inp, h, kv_cache, tpc)
-        h, residual = tpc.row_linear_add_norm(a, self.attn.o_w, residual, self.post_norm_w, eps)
+        h, residual = tpc.row_linear_add_norm(a, _qw(self.attn.o_w, self.attn.o_ws), residual, self.post_norm_w, eps)
         if self.is_moe:
             partial = self.mlp(tpc.materialize(h), tpc)
             if next_norm_w is None:
@@ -171,8 +178,8 @@ class DeepseekDecoderLayer(nn.Module):
             return tpc.reduce_add_norm(partial, residual, next_norm_w, eps)
         act = self.mlp.act(h, tpc)
         if next_norm_w is None:
-            return tpc.row_linear(act, self.mlp.down_w), residual
-        return tpc.row_linear_add_norm(act, self.mlp.down_w, residual, next_norm_w, eps)
+            return tpc.row_linear(act, self.mlp.down_weight()), residual
+        return tpc.row_linear_add_norm(act, self.mlp.down_weight(), residual, next_norm_w, eps)
 
 
 class DeepseekForCausalLM(CausalLM):
@@ -214,15 +221,15 @@ class DeepseekForCausalLM(CausalLM):
         tp, tr = self.tp_size, self.tp_rank
         p = pre + "self_attn."
         if at.q_lora:
-            at.q_a_w.data.copy_(reader.get(p + "q_a_proj.weight"))
+            _store_linear(at.q_a_w, at.q_a_ws, reader.get(p + "q_a_proj.weight"))
             at.q_a_norm_w.data.copy_(reader.get(p + "q_a_layernorm.weight"))
-            at.q_b_w.data.copy_(wu.shard_rows(reader.get(p + "q_b_proj.weight"), tr, tp))
+            _store_linear(at.q_b_w, at.q_b_ws, wu.shard_rows(reader.get(p + "q_b_proj.weight"), tr, tp))
         else:
-            at.q_w.data.copy_(wu.shard_rows(reader.get(p + "q_proj.weight"), tr, tp))
-        at.kv_a_w.data.copy_(reader.get(p + "kv_a_proj_with_mqa.weight"))
+            _store_linear(at.q_w, at.q_ws, wu.shard_rows(reader.get(p + "q_proj.weight"), tr, tp))
+        _store_linear(at.kv_a_w, at.kv_a_ws, reader.get(p + "kv_a_proj_with_mqa.weight"))
         at.kv_a_norm_w.data.copy_(reader.get(p + "kv_a_layernorm.weight"))
         at.kv_b_w.data.copy_(wu.shard_rows(reader.get(p + "kv_b_proj.weight"), tr, tp))
-        at.o_w.data.copy_(wu.shard_cols(reader.get(p + "o_proj.weight"), tr, tp))
+        _store_linear(at.o_w, at.o_ws, wu.shard_cols(reader.get(p + "o_proj.weight"), tr, tp))
 
 
 def spec_deepseek(cfg) -> ModelSpec:
@@ -263,8 +270,8 @@ def spec_deepseek(cfg) -> ModelSpec:
     spec.names = {"shared": "mlp.shared_experts.", "router_bias": "mlp.gate.e_score_correction_bias"}
     qc = cfg.get("quantization_config") or {}
     if qc.get("quant_method") == "fp8" and list(qc.get("weight_block_size") or []) == [128, 128]:
-        # the routed experts (97 % of the parameters) stay block-scaled e4m3 — that is what lets V3 / R1 fit on
-        # 8 x 180 GB; the MLA projections and the dense / shared MLPs are de-quantised to bf16 at load
+        # routed experts, MLA projections (q_a / q_b / kv_a / o) and dense / shared MLPs stay block-scaled e4m3 as in
+        # the checkpoint; kv_b_proj is de-quantised once into the bf16 W_UK / W_UV absorption operands
         spec.quant = "fp8"
     return spec
 

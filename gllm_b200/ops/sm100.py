@@ -321,6 +321,24 @@ def paged_attention(q: torch.Tensor, k_cache: torch.Tensor, v_cache: torch.Tenso
     return out
 
 
+def gemm_batched(a: torch.Tensor, w: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
+    """out[:, b, :] = a[:, b, :] @ w[b].T for every batch entry b, on the tcgen05 GEMM's batched mode
+    (csrc/gemm/gemm_bf16.cu): a [T, B, K] and out [T, B, N] may be strided views (last dim contiguous) — the operand
+    is read through a 3-D TMA map and the result written in place, no transposing copies; w [B, N, K] contiguous.
+    MLA weight absorption (per-head q_nope·W_UK and out_lat·W_UV) runs on this instead of a cuBLAS bmm."""
+    t, b, k = a.shape
+    n = w.shape[1]
+    assert w.shape == (b, n, k) and w.is_contiguous() and out.shape == (t, b, n)
+    assert a.dtype == _BF16 and w.dtype == _BF16 and out.dtype == _BF16
+    assert a.stride(2) == 1 and out.stride(2) == 1
+    L = _lib.load()
+    rc = L.gllm_gemm_bf16_batched(_p(a), a.stride(0), a.stride(1), _p(w), _p(out), out.stride(0), out.stride(1),
+                                  t, b, n, k, stream_ptr())
+    check(rc, "gemm_bf16_batched")
+    _count()
+    return out
+
+
 # ----------------------------------------------------------------------------------------------
 # sampling
 # ----------------------------------------------------------------------------------------------

@@ -268,6 +268,25 @@ def test_sampler_distribution():
     assert (emp - probs).abs().max().item() < 0.02
 
 
+@pytest.mark.parametrize("t", [1, 64, 300])
+@pytest.mark.parametrize("b,n,k", [(16, 512, 128), (16, 128, 512), (3, 256, 192)])
+def test_gemm_batched_strided_views(t, b, n, k):
+    """Batched mode of the tcgen05 GEMM (MLA weight absorption, K13): strided [T, B, K] operand through a 3-D TMA
+    map, result written into a strided [T, B, N] view, vs an fp32 einsum."""
+    from gllm_b200.ops import sm100
+    torch.manual_seed(t + n)
+    dev = _dev()
+    a_full = (torch.randn(t, b, k + 64, device=dev) * 0.5).bfloat16()     # the operand is a column slice
+    w = (torch.randn(b, n, k, device=dev) * 0.1).bfloat16()
+    out_full = torch.full((t, b, n + 64), 7.0, device=dev, dtype=torch.bfloat16)
+    a, out = a_full[:, :, :k], out_full[:, :, :n]
+    sm100.gemm_batched(a, w, out)
+    torch.cuda.synchronize()
+    ref_o = torch.einsum("tbk,bnk->tbn", a.float(), w.float())
+    assert _rel_err(out, ref_o) < 1e-2, _rel_err(out, ref_o)
+    assert bool((out_full[:, :, n:] == 7.0).all())                         # nothing written outside the view
+
+
 @pytest.mark.parametrize("tp", [2, 8])
 def test_vocab_parallel_sampling_equals_the_full_vocab_kernel(tp):
     """vp_candidates_kernel on each vocab shard + vp_final_kernel on the gathered records draw the
@@ -415,7 +434,8 @@ def test_moe_fused_experts(t, e, k, h, i, ep):
     assert _rel_err(y, y_ref) < 2e-2, _rel_err(y, y_ref)
 
 
-@pytest.mark.parametrize("m,n,k", [(1, 256, 128), (77, 1536, 512), (300, 4096, 7168), (1024, 2048, 2048)])
+@pytest.mark.parametrize("m,n,k", [(1, 256, 128), (77, 1536, 512), (300, 4096, 7168), (1024, 2048, 2048),
+                                   (64, 576, 7168)])      # 576 = kv_a_proj_with_mqa (MLA): N not a multiple of 128
 def test_gemm_fp8_block(m, n, k):
     from gllm_b200.ops import sm100
     torch.manual_seed(m)

@@ -26,6 +26,17 @@ import time
 sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 
 
+# BASELINE.json configurations: model preset, pipeline stages (tp = gpus / pp), schedule policy, metric label
+CONFIGS = {
+    "qwen3-8b-tp": dict(model="qwen3-8b", pp=1, method="chunked_prefill", label="Qwen3-8B TP"),
+    "mixtral-8x7b-ep": dict(model="mixtral-8x7b", pp=1, method="chunked_prefill", label="Mixtral-8x7B EP"),
+    "llama3-70b-pp4tp2": dict(model="llama-3-70b", pp=4, method="token_throttling",
+                              label="Llama-3-70B PP4xTP2 token-throttled"),
+    "deepseek-v3-fp8-ep": dict(model="deepseek-v3", pp=1, method="chunked_prefill",
+                               label="DeepSeek-V3 fp8 block-scaled EP"),
+}
+
+
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -41,6 +52,10 @@ def parse():
     ap.add_argument("--tp-mode", default="fused", choices=["fused", "nccl"])
     ap.add_argument("--schedule-method", default="chunked_prefill")
     ap.add_argument("--pp", type=int, default=1)
+    ap.add_argument("--config", default="qwen3-8b-tp", choices=sorted(CONFIGS),
+                    help="named BASELINE.json configuration (model + parallel layout + schedule policy)")
+    ap.add_argument("--layers", type=int, default=0, help="override num_hidden_layers (0 = the model's own); a "
+                    "reduced depth is reported in `config.model` and is NOT the named model")
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--async-schedule", action=argparse.BooleanOptionalAction, default=True,
                     help="lookahead decode scheduling (engine default; --no-async-schedule for the synchronous loop)")
@@ -198,8 +213,22 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     assert world == args.gpus or (world == 1 and args.gpus == 1), \
         f"--gpus {args.gpus} needs torchrun with {args.gpus} ranks (WORLD_SIZE={world})"
+    conf = CONFIGS[args.config]
+    model_name = args.model.replace("preset:", "")
+    model = args.model
+    if args.config != "qwen3-8b-tp":
+        model_name = conf["model"]
+        model = "preset:" + model_name
+        if args.pp == 1:
+            args.pp = min(conf["pp"], args.gpus)
+        if args.schedule_method == "chunked_prefill":
+            args.schedule_method = conf["method"]
+    if args.layers > 0:
+        from gllm_b200.models.presets import PRESETS
+        model = dict(PRESETS[model_name], num_hidden_layers=args.layers)
+        model_name = f"{model_name} REDUCED to {args.layers} layers"
     tp = args.gpus // args.pp
-    llm = LLM(args.model, load_format="dummy", tp_size=tp, pp_size=args.pp, maxp=args.maxp, maxd=args.maxd,
+    llm = LLM(model, load_format="dummy", tp_size=tp, pp_size=args.pp, maxp=args.maxp, maxd=args.maxd,
               max_cuda_graph_bs=args.max_cuda_graph_bs, schedule_method=args.schedule_method,
               enable_prefix_caching=True, gpu_memory_util=0.9, model_max_length=2048 + 16,
               tp_mode=args.tp_mode, log_stats=False, launch_mode="inproc", seed=args.seed,
@@ -283,13 +312,13 @@ def main():
         except Exception:  # noqa: BLE001
             pass
         out = {
-            "metric": "output tokens/sec, offline throughput (benchmark_throughput workload), Qwen3-8B TP",
+            "metric": "output tokens/sec, offline throughput (benchmark_throughput workload), " + conf["label"],
             "value": round(value, 1), "unit": "tokens/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": round(dev_ms / args.steps, 2), "higher_is_better": True,
             "scaling": "strong", "vs_baseline": (value / base) if base else None, "dtype": "bf16",
             "data": "synthetic ShareGPT-shaped token ids (log-normal lengths, reference dataset filter); random-init weights",
             "impl": "ours",
-            "config": {"model": args.model.replace("preset:", ""), "num_prompts": args.num_prompts,
+            "config": {"model": model_name, "named_config": args.config, "num_prompts": args.num_prompts,
                        "global_batch": args.num_prompts, "seq_len": "prompt<=1024, prompt+output<=2048",
                        "input_tokens_per_step": total_in, "output_tokens_per_step": total_out,
                        "parallelism": f"tp{tp}" + (f"pp{args.pp}" if args.pp > 1 else ""), "tp_mode": args.tp_mode,

@@ -88,10 +88,22 @@ async def run(args):
         async with sem:
             return await fn(inp, pbar)
 
+    if args.prompt_format == "words":
+        # servers that only take text (the reference's /v1/completions tokenises `prompt`): the benchmark model
+        # directories carry a one-word-per-id vocabulary ("t<id>"), so the same token ids go over the wire as words
+        prompts = [" ".join(f"t{t}" for t in p) for p in prompts]
     t0 = time.perf_counter()
     tasks = []
-    async for i in arrival_times(len(prompts), args.request_rate, args.burstiness, rng):
-        tasks.append(asyncio.create_task(one(i)))
+    # staged arrivals (reference: benchmarks/benchmark_serving.py:686-718): the request set is cut into
+    # `--arrival-stage` equal parts, each sent with its own Poisson process, `--stage-interval` seconds apart
+    n_stage = max(1, args.arrival_stage)
+    per = len(prompts) // n_stage
+    for st in range(n_stage):
+        lo, hi = st * per, (st + 1) * per if st != n_stage - 1 else len(prompts)
+        async for i in arrival_times(hi - lo, args.request_rate, args.burstiness, rng):
+            tasks.append(asyncio.create_task(one(lo + i)))
+        if n_stage != 1:
+            await asyncio.sleep(args.stage_interval)
     results = await asyncio.gather(*tasks)
     dur = time.perf_counter() - t0
     pbar.close()
@@ -102,7 +114,8 @@ async def run(args):
     if args.goodput:
         goodput = {kv.split(":")[0]: float(kv.split(":")[1]) for kv in args.goodput}
     res = summarise(results, dur, [float(p) for p in args.metric_percentiles.split(",")], goodput)
-    res.update({"backend": args.backend, "request_rate": args.request_rate, "num_prompts": args.num_prompts})
+    res.update({"backend": args.backend, "request_rate": args.request_rate, "num_prompts": args.num_prompts,
+                "arrival_stage": args.arrival_stage, "stage_interval": args.stage_interval})
     print("{s:=^50}".format(s=" Serving Benchmark Result "))
     for k, v in res.items():
         print(f"{k:<32}{v}")
@@ -129,6 +142,10 @@ def main():
     ap.add_argument("--max-output-len", type=int, default=512)
     ap.add_argument("--vocab-size", type=int, default=150000)
     ap.add_argument("--seed", type=int, default=0)
+    ap.add_argument("--prompt-format", default="ids", choices=["ids", "words"],
+                    help="send prompts as token-id lists, or as 't<id>' words for text-only servers")
+    ap.add_argument("--arrival-stage", type=int, default=1, help="number of stages the requests are sent in")
+    ap.add_argument("--stage-interval", type=float, default=10.0, help="seconds between stages")
     ap.add_argument("--metric-percentiles", default="50,90,99")
     ap.add_argument("--goodput", nargs="*", default=None, help="SLOs like ttft:500 tpot:50 e2el:10000 (ms)")
     ap.add_argument("--profile", action="store_true")

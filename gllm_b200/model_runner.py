@@ -91,8 +91,12 @@ class ModelRunner:
         t0 = time.time()
         self.model = self.loader.load_model(self.device, progress)
         self.spec = self.model.spec
-        self.tpc = make_tp_comm(fused=(cfg.tp_mode == "fused" and getattr(self.spec, "quant", None) is None
-                                       and not getattr(self.model, "num_deepstack", 0)),
+        want_fused = cfg.tp_mode == "fused" and cfg.tp_size > 1 and is_cuda
+        why_not = "fp8 block-scaled linears" if getattr(self.spec, "quant", None) is not None else \
+            "DeepStack (Qwen3-VL) feature injection" if getattr(self.model, "num_deepstack", 0) else None
+        if want_fused and why_not:
+            logger.warning("tp_mode=fused is not available with %s: tensor-parallel collectives run on NCCL", why_not)
+        self.tpc = make_tp_comm(fused=(want_fused and why_not is None),
                                 max_tokens=self.max_num_batched_tokens,
                                 hidden_size=self.spec.hidden_size, dtype=self.spec.dtype, device=self.device) \
             if cfg.tp_size > 1 else make_tp_comm(False)

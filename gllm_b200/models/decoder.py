@@ -324,7 +324,17 @@ class CausalLM(nn.Module):
                         for w in works:
                             w.wait()
                 return hidden, residual
-            if recv_tiles and len(recv_tiles) > 1 and hasattr(self.layers[0].attn, "qkv_proj"):
+            if getattr(tpc, "fused", False):
+                # fused TP inside a pipeline stage: the stage input arrives replicated; fold the previous stage's
+                # block output into the residual stream, then enter the token-sharded dataflow exactly like the
+                # embedding output does on the first stage (normed gather buffer + residual shard)
+                if recv_tiles:
+                    for _, _, works in recv_tiles:
+                        for w in works:
+                            w.wait()
+                _, res_full = Fn.rmsnorm(hidden, self.layers[0].input_norm_w, eps, residual)
+                h, residual = tpc.first_norm(res_full, self.layers[0].input_norm_w, eps)
+            elif recv_tiles and len(recv_tiles) > 1 and hasattr(self.layers[0].attn, "qkv_proj"):
                 # tile-streamed pipeline input: add+RMSNorm and the QKV GEMM run per row tile as the tiles
                 # land, overlapping the NCCL transfer of the following tiles
                 h = torch.empty_like(hidden)
@@ -365,6 +375,8 @@ class CausalLM(nn.Module):
                 h, residual = layer(inp, h, residual, kv_cache, tpc, nxt)
         if nvtx and n:
             torch.cuda.nvtx.range_pop()
+        if not self.is_last:
+            residual = tpc.stage_exit(residual)
         return h, residual
 
     def compute_logits(self, inp, hidden: torch.Tensor, tpc: TPComm, all_rows: bool = False,

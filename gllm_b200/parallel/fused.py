@@ -241,6 +241,14 @@ class FusedTPComm(TPComm):
             return super().first_norm(x, norm_w, eps)
         return self._reduce_norm(0, 0, x, False, norm_w, eps)
 
+    def stage_exit(self, residual):
+        """Pipeline stage boundary: inside a stage the residual stream is token-sharded (each rank owns `rpr` rows);
+        the next stage receives it replicated, so gather the shards (once per stage and step, on NCCL)."""
+        if residual is None or self.small:
+            return residual
+        full = ps.tp_all_gather_first_dim(residual[: self.rpr].contiguous())
+        return full[: self.T]
+
     def materialize(self, h: torch.Tensor) -> torch.Tensor:
         """Make the gather buffer safe to read by a kernel that does not understand the flags."""
         if not self.small and self.cur_ag is not None and h.data_ptr() == self.cur_ag[1].data_ptr():

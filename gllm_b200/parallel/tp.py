@@ -44,6 +44,10 @@ class TPComm:
         """Make `h` safe to read by kernels that are not collective-aware (no-op here)."""
         return h
 
+    def stage_exit(self, residual: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
+        """Residual stream in the replicated [T, H] form a pipeline stage boundary ships (no-op here)."""
+        return residual
+
     def col_linear(self, x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None) -> torch.Tensor:
         return Fn.linear(x, w, bias)
 
@@ -89,7 +93,7 @@ class TPComm:
 
 def make_tp_comm(fused: bool = False, **kw) -> TPComm:
     st = ps.get_state()
-    if fused and st.tp_size > 1 and st.pp_size == 1 and torch.cuda.is_available():
+    if fused and st.tp_size > 1 and torch.cuda.is_available():
         from gllm_b200.parallel.fused import FusedTPComm
         return FusedTPComm(**kw)
     return TPComm()

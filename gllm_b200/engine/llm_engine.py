@@ -435,23 +435,40 @@ class LLM:
                 p.terminate()
         self.procs = []
         if comm is not None:
-            comm.close(unlink_all=True)   # after the workers are gone: nobody is left to re-create the ipc files
+            # after the workers are gone nobody is left to re-create the ipc files, so the front-end removes all of
+            # them — except under an external launcher (torchrun): there every rank is alive and cleans up its own
+            # endpoints; a rank that is already building its next engine must not lose the sockets it just bound
+            comm.close(unlink_all=not self.is_external)
 
     def close(self):
         """Full teardown for an orderly process exit: stop the workers, then release device-side state that other
         ranks map (CUDA graphs first — they reference the peers' buffers —, then the symmetric-memory handles).
         Collective when tp > 1: every rank calls it, peers still alive."""
         worker = self.worker
+        world = self.is_external and torch_dist_ready()
+        if world:
+            import torch.distributed as dist
+            dist.barrier()          # nobody tears sockets down while a peer is still serving
         self.shutdown()
         runner = getattr(worker, "runner", None) if worker is not None else None
         if runner is not None:
             runner.close()
+        if world:
+            dist.barrier()          # ... and nobody builds the next engine before everyone has let go of this one
 
     def __del__(self):
         try:
             self.shutdown()
         except Exception:  # noqa: BLE001
             pass
+
+
+def torch_dist_ready() -> bool:
+    try:
+        import torch.distributed as dist
+        return dist.is_available() and dist.is_initialized()
+    except Exception:  # noqa: BLE001
+        return False
 
 
 class _NoFrontend:

@@ -12,6 +12,9 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
 
 def main():
+    import faulthandler
+    # a stuck collective must leave evidence: dump every thread's stack and exit instead of waiting for the caller
+    faulthandler.dump_traceback_later(int(os.environ.get("GLLM_TP_CHECK_TIMEOUT", "420")), exit=True)
     rank, local, world = int(os.environ["RANK"]), int(os.environ["LOCAL_RANK"]), int(os.environ["WORLD_SIZE"])
     torch.cuda.set_device(local)
     from gllm_b200.parallel import state as ps

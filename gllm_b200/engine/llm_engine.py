@@ -49,6 +49,8 @@ def load_tokenizer(path):
 
 
 class LLM:
+    _instances = 0      # engines created by this process (names the ipc endpoints of each one)
+
     def __init__(self, model_path, host=None, master_addr="127.0.0.1", master_port=8001, zmq_port_base=8002,
                  launch_mode="normal", worker_ranks=None, load_format="auto", gpu_memory_util=0.9, page_size=16,
                  maxd=2048, maxp=2048, minp=32, iterp=8, kvthresh=0.05, enable_prefix_caching=True, pp_size=1,
@@ -113,7 +115,12 @@ class LLM:
             rank, local_rank = (self.env_rank, self.env_local_rank) if self.is_external else (0, 0)
             comm = None
             if cfg.world_size > 1:
-                base = ipc_base(f"p{cfg.master_port}")
+                # one set of ipc endpoints per engine INSTANCE: ranks create their engines in lockstep, so the counter
+                # agrees across ranks. Re-using the file names of a previous engine of this process is unsafe — zmq
+                # closes sockets asynchronously and a listener unlinks its ipc file when it finally goes away, which
+                # can be after the next engine has bound the same path (its peers then never hear from the driver).
+                LLM._instances += 1
+                base = ipc_base(f"p{cfg.master_port}_{LLM._instances}")
                 comm = Comm(base, rank, cfg.world_size, (cfg.pp_size - 1) * cfg.tp_size, frontend=False)
                 comm.sock_fe_in = comm.sock_fe_out = None
             self.worker = Worker(cfg, rank, local_rank, comm=_NoFrontend(comm) if comm else None,

@@ -149,7 +149,10 @@ class ModelRunner:
         n = max(1, min(self.max_running_seqs, t))
         batch = _dummy_batch(t, n, self.page_size, self.input_data.max_blocks)
         torch.cuda.synchronize()
-        self._forward(batch, None, None, use_kv=False)
+        hidden = residual = None
+        if not ps.is_first_pp_rank():     # later stages start from the previous stage's (hidden, residual)
+            hidden, residual = self.input_hidden[:t], self.input_residual[:t]
+        self._forward(batch, hidden, residual, use_kv=False)
         torch.cuda.synchronize()
 
     def compute_num_pages(self) -> int:

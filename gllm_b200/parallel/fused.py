@@ -61,7 +61,9 @@ class EpArgs(ctypes.Structure):
 
 _ONESHOT = os.environ.get("GLLM_TP_ONESHOT", "1") != "0"
 MAX_BLOCKS = 256   # kMaxBlocks in csrc/comm/tp_fused.cu (128-row blocks per gather buffer)
-SMALL_T = 64       # forwards with <= this many tokens use the NCCL strategy (see begin_forward)
+SMALL_T = int(os.environ.get("GLLM_TP_SMALL_T", "64"))   # forwards with <= this many tokens: replicated rows +
+# one-kernel LL all-reduce⊕add⊕norm instead of the token-sharded GEMM⊕RS / AG⊕GEMM dataflow (see begin_forward;
+# calibrated with benchmarks/tp_small_t_sweep.py)
 
 
 def _declare(L):

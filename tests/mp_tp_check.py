@@ -13,8 +13,22 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
 def main():
     import faulthandler
-    # a stuck collective must leave evidence: dump every thread's stack and exit instead of waiting for the caller
-    faulthandler.dump_traceback_later(int(os.environ.get("GLLM_TP_CHECK_TIMEOUT", "420")), exit=True)
+    import threading
+    # a stuck collective must leave evidence: dump every thread's stack (and what the engine on this rank has done so
+    # far) and exit instead of waiting for the caller
+    limit = int(os.environ.get("GLLM_TP_CHECK_TIMEOUT", "420"))
+    faulthandler.dump_traceback_later(limit, exit=True)
+
+    def _where():
+        llm = globals().get("_LIVE_LLM")
+        if llm is not None and llm.worker is not None and llm.worker.runner is not None:
+            w = llm.worker
+            print(f"[stall rank {os.environ.get('RANK')}] runner steps {w.runner.stats['steps']} graph_steps "
+                  f"{w.runner.stats['graph_steps']} queued peer batches {len(w.peer_batches)} pending {len(w.pending)} "
+                  f"batch_counter {w.batch_counter}", flush=True)
+    t = threading.Timer(max(limit - 5, 1), _where)
+    t.daemon = True
+    t.start()
     rank, local, world = int(os.environ["RANK"]), int(os.environ["LOCAL_RANK"]), int(os.environ["WORLD_SIZE"])
     torch.cuda.set_device(local)
     from gllm_b200.parallel import state as ps
@@ -150,14 +164,18 @@ def main():
                            num_local_experts=8, num_experts_per_tok=2, torch_dtype="bfloat16"),
     }
     prompts = [[5, 9, 100, 7], list(range(20, 190)), [77] * 33, [3, 1, 4, 1, 5, 9, 2, 6]]
-    os.environ["GLLM_KEEP_LOGITS"] = "1"      # the runner keeps every step's last-token logits (all ranks: collective)
+    # the runner keeps every step's last-token logits (all ranks: collective)
+    os.environ["GLLM_KEEP_LOGITS"] = os.environ.get("GLLM_TP_CHECK_LOGITS", "1")
+    keep = os.environ["GLLM_KEEP_LOGITS"] == "1"
     n_out = 8
     for name, cfg in cfgs.items():
         toks, logs = {}, {}
         for mode in ("nccl", "fused"):
             torch.manual_seed(4321 + rank)
             llm = LLM(cfg, load_format="dummy", tp_size=world, maxp=128, maxd=64, max_cuda_graph_bs=8,
-                      num_gpu_pages=256, model_max_length=512, log_stats=False, tp_mode=mode, launch_mode="inproc")
+                      num_gpu_pages=256, model_max_length=512, log_stats=False, tp_mode=mode, launch_mode="inproc",
+                      async_schedule=os.environ.get("GLLM_TP_CHECK_ASYNC", "1") == "1")
+            globals()["_LIVE_LLM"] = llm
             outs = llm.generate(tokens=prompts, output_lens=[n_out] * len(prompts), ignore_eos=True)
             if rank == 0:
                 toks[mode] = [s.token_ids[len(p):] for s, p in zip(outs, prompts)]
@@ -171,7 +189,10 @@ def main():
             if mode == "fused" and name == "mixtral-ep":
                 assert llm.worker.runner.tpc.ep is not None, "EP all-to-all path did not run"
             llm.close()
-        if rank == 0:
+        if rank == 0 and not keep:
+            agree = sum(a == b for x, y in zip(toks["nccl"], toks["fused"]) for a, b in zip(x, y))
+            print(name, f"token agreement {agree}/{n_out * len(prompts)} (logits check disabled)", flush=True)
+        if rank == 0 and keep:
             # Logits-based criterion: as long as a sequence's tokens agree between the two modes its inputs are
             # identical, so the last-token logits of that step must agree to bf16 accumulation-order noise; and
             # where the greedy tokens first differ, it has to be a genuine near-tie in BOTH modes' logits.

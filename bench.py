@@ -59,6 +59,8 @@ def parse():
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--async-schedule", action=argparse.BooleanOptionalAction, default=True,
                     help="lookahead decode scheduling (engine default; --no-async-schedule for the synchronous loop)")
+    ap.add_argument("--disable-cuda-graph", action="store_true", help="debugging: every step runs eagerly")
+    ap.add_argument("--num-gpu-pages", type=int, default=None, help="debugging: fixed KV pool size (pages)")
     ap.add_argument("--fixed-prompts", action="store_true",
                     help="re-use the same token ids in every pass (with prefix caching the prompts of later passes "
                          "would then be served from the cache: NOT the benchmark; for debugging only)")
@@ -232,7 +234,8 @@ def main():
               max_cuda_graph_bs=args.max_cuda_graph_bs, schedule_method=args.schedule_method,
               enable_prefix_caching=True, gpu_memory_util=0.9, model_max_length=2048 + 16,
               tp_mode=args.tp_mode, log_stats=False, launch_mode="inproc", seed=args.seed,
-              async_schedule=args.async_schedule)
+              async_schedule=args.async_schedule, disable_cuda_graph=args.disable_cuda_graph,
+              num_gpu_pages=args.num_gpu_pages)
     vocab = llm.loader.config["vocab_size"]
     prompts, out_lens = synth_requests(args.num_prompts, vocab, args.seed)
     total_out = sum(out_lens)

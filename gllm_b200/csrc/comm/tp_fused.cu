@@ -30,7 +30,8 @@ struct TpState {
   uint32_t ag_epoch[3];             // per gather buffer: number of pushes so far (diagnostic)
   uint32_t ticket[4];               // grid tickets
   uint32_t ll_epoch;                // one-shot LL all-reduce: calls completed so far (flag value of the next call - 1)
-  uint32_t pad[8];                  // -> ag_expected starts at byte 128
+  uint32_t nvls_epoch;              // NVLS (multimem) all-reduce: calls completed so far
+  uint32_t pad[7];                  // -> ag_expected starts at byte 128
   // per gather buffer, per 128-row block: rows that must have arrived before the block may be read.
   // Arrival counters (symmetric `flags`) are bumped once per pushed row by the row's owner, so a
   // consumer GEMM can start on the blocks that are complete while the rest is still in flight.
@@ -347,6 +348,123 @@ __global__ void ll_allreduce_norm_kernel(const LLParams p) {
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// NVLS one-shot all-reduce ⊕ residual add ⊕ RMSNorm: the reduction happens INSIDE the NVSwitch. Every rank stores its
+// partial row into its own slice of a symmetric buffer that is also mapped as a multicast object, publishes
+// "row r of rank s is written" with ONE multimem.red on a multicast flag (lands in every rank's flag array), waits
+// until all tp sources have published the row, and then reads the row through the multicast address with
+// multimem.ld_reduce: the switch fetches the tp replicas and returns their fp32-accumulated sum. Per rank and row
+// that is H*2 bytes in and H*2 bytes out over NVLink, independent of tp — the LL variant above receives
+// (tp-1) * H * 4 bytes. Replaces NCCL all_reduce + add + norm of the reference (gllm/layers/linear.py:247-250,
+// gllm/layers/layernorm.py) for decode-sized batches when the fabric supports multicast.
+// ------------------------------------------------------------------------------------------------------------------
+struct NvlsParams {
+  const __nv_bfloat16* x;      // this rank's partial [T, H]
+  int64_t ldx;
+  __nv_bfloat16* residual;     // [T, H] replicated running residual (in/out)
+  int residual_in;
+  const __nv_bfloat16* norm_w;
+  __nv_bfloat16* out;          // [T, H] normed output (local)
+  __nv_bfloat16* buf_local;    // this rank's [row_cap, H] slice for this parity (unicast address)
+  const __nv_bfloat16* buf_mc; // the same slice through the multicast mapping
+  uint32_t* flags_mc;          // [tp][row_cap] epoch flags, multicast address (a store reaches every rank)
+  const uint32_t* flags_local; // this rank's copy of the flags (unicast address)
+  TpState* st;
+  int tp, rank, T, H, row_cap;
+  float eps;
+};
+
+__device__ __forceinline__ void multimem_red_max_release(uint32_t* mc_addr, uint32_t v) {
+  asm volatile("multimem.red.release.sys.global.max.u32 [%0], %1;" ::"l"(mc_addr), "r"(v) : "memory");
+}
+// 8 bf16 (16 bytes) of the sum over all replicas, accumulated in fp32 inside the switch
+__device__ __forceinline__ uint4 multimem_ld_reduce_bf16x8(const void* mc_addr) {
+  uint4 v;
+  asm volatile("multimem.ld_reduce.relaxed.sys.global.add.acc::f32.v4.bf16x2 {%0, %1, %2, %3}, [%4];"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+               : "l"(mc_addr)
+               : "memory");
+  return v;
+}
+
+__global__ void nvls_allreduce_norm_kernel(const NvlsParams p) {
+  __shared__ float red[32];
+  griddep_launch();
+  griddep_wait();
+  const int row = blockIdx.x;
+  const int tid = threadIdx.x;
+  const bool active = tid * 8 < p.H;
+  const uint32_t epoch = *reinterpret_cast<const volatile uint32_t*>(&p.st->nvls_epoch) + 1u;
+  const size_t off = static_cast<size_t>(row) * p.H + tid * 8;
+  if (active) {
+    const uint4 v = *reinterpret_cast<const uint4*>(p.x + static_cast<size_t>(row) * p.ldx + tid * 8);
+    *reinterpret_cast<uint4*>(p.buf_local + off) = v;
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (tid == 0) {
+    // one instruction tells every rank that this rank's row is in place (max: the flag only ever moves forward)
+    multimem_red_max_release(p.flags_mc + p.rank * p.row_cap + row, epoch);
+    SpinGuard guard;
+    for (int s = 0; s < p.tp; ++s) {
+      while (static_cast<int32_t>(ld_acquire_sys(p.flags_local + s * p.row_cap + row) - epoch) < 0) guard.poll();
+    }
+  }
+  __syncthreads();
+  float a[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (active) {
+    const uint4 v = multimem_ld_reduce_bf16x8(p.buf_mc + off);
+    const float2 f0 = unpack_bf16(v.x), f1 = unpack_bf16(v.y), f2 = unpack_bf16(v.z), f3 = unpack_bf16(v.w);
+    a[0] = f0.x; a[1] = f0.y; a[2] = f1.x; a[3] = f1.y; a[4] = f2.x; a[5] = f2.y; a[6] = f3.x; a[7] = f3.y;
+  }
+  float ss = 0.f;
+  if (active) {
+    __nv_bfloat16* rp = p.residual + off;
+    if (p.residual_in) {
+      const uint4 r = *reinterpret_cast<const uint4*>(rp);
+      const float2 r0 = unpack_bf16(r.x), r1 = unpack_bf16(r.y), r2 = unpack_bf16(r.z), r3 = unpack_bf16(r.w);
+      a[0] += r0.x; a[1] += r0.y; a[2] += r1.x; a[3] += r1.y; a[4] += r2.x; a[5] += r2.y; a[6] += r3.x; a[7] += r3.y;
+    }
+    uint4 o;
+    o.x = pack_bf16(a[0], a[1]); o.y = pack_bf16(a[2], a[3]); o.z = pack_bf16(a[4], a[5]); o.w = pack_bf16(a[6], a[7]);
+    *reinterpret_cast<uint4*>(rp) = o;
+    const float2 q0 = unpack_bf16(o.x), q1 = unpack_bf16(o.y), q2 = unpack_bf16(o.z), q3 = unpack_bf16(o.w);
+    a[0] = q0.x; a[1] = q0.y; a[2] = q1.x; a[3] = q1.y; a[4] = q2.x; a[5] = q2.y; a[6] = q3.x; a[7] = q3.y;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) ss += a[e] * a[e];
+  }
+  {
+    const int lane = tid & 31, warp = tid >> 5;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    if (lane == 0) red[warp] = ss;
+    __syncthreads();
+    float t = lane < ((blockDim.x + 31) >> 5) ? red[lane] : 0.f;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    ss = t;
+  }
+  if (active) {
+    const float inv = rsqrtf(ss / static_cast<float>(p.H) + p.eps);
+    const uint4 wv = *reinterpret_cast<const uint4*>(p.norm_w + tid * 8);
+    const float2 w0 = unpack_bf16(wv.x), w1 = unpack_bf16(wv.y), w2 = unpack_bf16(wv.z), w3 = unpack_bf16(wv.w);
+    uint4 o;
+    o.x = pack_bf16(a[0] * inv * w0.x, a[1] * inv * w0.y);
+    o.y = pack_bf16(a[2] * inv * w1.x, a[3] * inv * w1.y);
+    o.z = pack_bf16(a[4] * inv * w2.x, a[5] * inv * w2.y);
+    o.w = pack_bf16(a[6] * inv * w3.x, a[7] * inv * w3.y);
+    *reinterpret_cast<uint4*>(p.out + off) = o;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    const uint32_t old = atomicAdd(&p.st->ticket[2], 1u);
+    if (old == gridDim.x - 1) {       // last CTA closes the epoch
+      p.st->ticket[2] = 0u;
+      p.st->nvls_epoch = epoch;
+    }
+  }
+}
+
 // Push a full-length partial [T, H] (e.g. the MoE block output, or anything not produced by the fused
 // GEMM epilogue) into the owners' staging slots; one CTA per row, one arrival per row.
 __global__ void push_partial_rows_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, int T, int H, int rank,
@@ -495,6 +613,44 @@ GLLM_EXPORT int gllm_ll_allreduce_norm(const LLArgs* a, void* stream) {
   p.tp = a->tp; p.rank = a->rank; p.T = a->T; p.H = a->H; p.row_cap = a->row_cap; p.eps = a->eps;
   const int threads = ((a->H / 8 + 31) / 32) * 32;
   CUDA_CHECK_RET(launch_pdl(ll_allreduce_norm_kernel, dim3(a->T), dim3(threads), 0,
+                            reinterpret_cast<cudaStream_t>(stream), p));
+  return 0;
+}
+
+struct NvlsArgs {
+  const void* x;
+  int64_t ldx;
+  void* residual;
+  int residual_in;
+  const void* norm_w;
+  void* out;
+  void* buf_local;
+  const void* buf_mc;
+  void* flags_mc;
+  const void* flags_local;
+  void* st;
+  int tp, rank, T, H, row_cap;
+  float eps;
+};
+
+GLLM_EXPORT int gllm_nvls_allreduce_norm(const NvlsArgs* a, void* stream) {
+  if (a->T <= 0) return 0;
+  if (a->H % 8 != 0 || a->H / 8 > 1024 || a->T > a->row_cap || a->tp > kMaxTp) return 1;
+  NvlsParams p;
+  p.x = reinterpret_cast<const __nv_bfloat16*>(a->x);
+  p.ldx = a->ldx;
+  p.residual = reinterpret_cast<__nv_bfloat16*>(a->residual);
+  p.residual_in = a->residual_in;
+  p.norm_w = reinterpret_cast<const __nv_bfloat16*>(a->norm_w);
+  p.out = reinterpret_cast<__nv_bfloat16*>(a->out);
+  p.buf_local = reinterpret_cast<__nv_bfloat16*>(a->buf_local);
+  p.buf_mc = reinterpret_cast<const __nv_bfloat16*>(a->buf_mc);
+  p.flags_mc = reinterpret_cast<uint32_t*>(a->flags_mc);
+  p.flags_local = reinterpret_cast<const uint32_t*>(a->flags_local);
+  p.st = reinterpret_cast<TpState*>(a->st);
+  p.tp = a->tp; p.rank = a->rank; p.T = a->T; p.H = a->H; p.row_cap = a->row_cap; p.eps = a->eps;
+  const int threads = ((a->H / 8 + 31) / 32) * 32;
+  CUDA_CHECK_RET(launch_pdl(nvls_allreduce_norm_kernel, dim3(a->T), dim3(threads), 0,
                             reinterpret_cast<cudaStream_t>(stream), p));
   return 0;
 }

@@ -243,10 +243,15 @@ def decode_splits(num_seqs: int, num_kv_heads: int, num_q_heads: int, max_seq_le
     return max(1, min(s, max_tiles))
 
 
+_retired = []   # outgrown workspaces stay alive: CUDA graphs captured earlier may still point at them
+
+
 def _workspace(device, n_floats: int, tag: str) -> torch.Tensor:
     key = (device, tag)
     ws = _attn_ws.get(key)
     if ws is None or ws.numel() < n_floats:
+        if ws is not None:
+            _retired.append(ws)
         ws = torch.empty(max(n_floats, 1 << 20), dtype=torch.float32, device=device)
         _attn_ws[key] = ws
     return ws
@@ -257,6 +262,8 @@ def _split_counters(device, n: int) -> torch.Tensor:
     key = (device, "split_cnt")
     c = _attn_ws.get(key)
     if c is None or c.numel() < n:
+        if c is not None:
+            _retired.append(c)
         c = torch.zeros(max(n, 1 << 16), dtype=torch.int32, device=device)
         _attn_ws[key] = c
     return c
@@ -267,6 +274,8 @@ def reserve_attn_workspace(device, max_seqs: int, num_q_heads: int, head_dim: in
     _workspace(device, max_seqs * num_q_heads * max_splits * head_dim, "part_o")
     _workspace(device, max_seqs * num_q_heads * max_splits, "part_lse")
     _split_counters(device, max_seqs * num_q_heads)
+    if head_dim == 576:      # MLA latent attention: its own split-KV partials
+        _mla_workspace(device, num_q_heads)
 
 
 def paged_attention(q: torch.Tensor, k_cache: torch.Tensor, v_cache: torch.Tensor, block_table: torch.Tensor,
@@ -452,6 +461,23 @@ def mla_splits(tokens: int, heads: int) -> int:
     return max(1, min(16, 296 // ctas))
 
 
+def _mla_workspace(device, heads: int):
+    """Split-KV partials of the MLA kernel, allocated ONCE per device (never re-allocated: CUDA graphs captured
+    earlier keep writing to it — a lazily grown buffer was freed under them and a later replay faulted). Capacity:
+    a forward splits only while tokens * ceil(heads/16) * splits <= 296 CTAs (`mla_splits`), i.e. at most
+    296 * 16 (token, head, split) rows, or 16 splits of one token's heads."""
+    key = ("mla_ws", torch.device(device))
+    ws = _attn_ws.get(key)
+    rows = max(296 * 16, 16 * heads)
+    if ws is None or ws[1].numel() < rows:
+        assert not (torch.cuda.is_available() and torch.cuda.is_current_stream_capturing()), \
+            "reserve_attn_workspace() must run before CUDA-graph capture"
+        ws = (torch.empty(rows * 512, dtype=torch.float32, device=device),
+              torch.empty(rows, dtype=torch.float32, device=device))
+        _attn_ws[key] = ws
+    return ws
+
+
 def mla_rope_cache(q_pe: torch.Tensor, q_full: torch.Tensor, k_pe: torch.Tensor, kv_c: torch.Tensor,
                    cos_sin: torch.Tensor, positions: torch.Tensor, slots: torch.Tensor, cache: torch.Tensor):
     """q_pe [T,H,64] (strided view), q_full [T,H,576] (rope part written), k_pe [T,64], kv_c [T,512];
@@ -483,14 +509,11 @@ def mla_attention(q_full: torch.Tensor, cache: torch.Tensor, block_table: torch.
     out = torch.empty(t, h, 512, dtype=_BF16, device=q_full.device)
     part_o = part_lse = None
     if splits > 1:
-        key = ("mla_ws", q_full.device)
-        need = t * h * splits
-        ws = _attn_ws.get(key)
-        if ws is None or ws[0].numel() < need * 512:
-            ws = (torch.empty(need * 512, dtype=torch.float32, device=q_full.device),
-                  torch.empty(need, dtype=torch.float32, device=q_full.device))
-            _attn_ws[key] = ws
-        part_o, part_lse = ws
+        if t * h * splits > max(296 * 16, 16 * h):
+            splits = max(1, max(296 * 16, 16 * h) // (t * h))      # caller-forced split beyond the workspace
+    if splits > 1:
+        part_o, part_lse = _mla_workspace(q_full.device, h)
+        assert t * h * splits <= part_lse.numel()
     L = _lib.load()
     check(L.gllm_mla_attention(_p(q_full), _p(out), _p(cache), pages, _p(block_table), _p(tok_seq), _p(positions),
                                _p(part_o), _p(part_lse), t, block_table.shape[1], h, page_size, splits, float(scale),

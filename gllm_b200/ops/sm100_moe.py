@@ -18,6 +18,7 @@ from gllm_b200.ops.sm100 import _count, _p
 
 _BF16 = torch.bfloat16
 _ws = {}
+_retired = []
 
 
 def _buf(key, shape, dtype, device, zero=False):
@@ -27,6 +28,8 @@ def _buf(key, shape, dtype, device, zero=False):
     for s in shape:
         n *= s
     if t is None or t.numel() < n or t.dtype != dtype:
+        if t is not None:
+            _retired.append(t)     # a CUDA graph captured earlier may still point at the outgrown buffer
         t = (torch.zeros if zero else torch.empty)(max(n, 1), dtype=dtype, device=device)
         _ws[k] = t
     return t[:n].view(*shape)

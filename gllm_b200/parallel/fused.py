@@ -51,6 +51,14 @@ class LLArgs(ctypes.Structure):
                 ("tp", c_int), ("rank", c_int), ("T", c_int), ("H", c_int), ("row_cap", c_int), ("eps", c_float)]
 
 
+class NvlsArgs(ctypes.Structure):
+    """Mirror of `NvlsArgs` in csrc/comm/tp_fused.cu (in-switch multimem all-reduce + add + RMSNorm)."""
+    _fields_ = [("x", c_void_p), ("ldx", c_int64), ("residual", c_void_p), ("residual_in", c_int),
+                ("norm_w", c_void_p), ("out", c_void_p), ("buf_local", c_void_p), ("buf_mc", c_void_p),
+                ("flags_mc", c_void_p), ("flags_local", c_void_p), ("st", c_void_p),
+                ("tp", c_int), ("rank", c_int), ("T", c_int), ("H", c_int), ("row_cap", c_int), ("eps", c_float)]
+
+
 class EpArgs(ctypes.Structure):
     """Mirror of `EpArgs` in csrc/comm/ep_a2a.cu."""
     _fields_ = [("recv_x", c_void_p * MAX_PEERS), ("recv_e", c_void_p * MAX_PEERS),
@@ -77,6 +85,8 @@ def _declare(L):
     L.gllm_tp_state_bytes.restype = c_int
     L.gllm_ll_allreduce_norm.argtypes = [ctypes.POINTER(LLArgs), c_void_p]
     L.gllm_ll_allreduce_norm.restype = c_int
+    L.gllm_nvls_allreduce_norm.argtypes = [ctypes.POINTER(NvlsArgs), c_void_p]
+    L.gllm_nvls_allreduce_norm.restype = c_int
     L.gllm_ep_state_bytes.argtypes = []
     L.gllm_ep_state_bytes.restype = c_int
     L.gllm_ep_dispatch.argtypes = [ctypes.POINTER(EpArgs), c_void_p, c_int64, c_void_p, c_int, c_void_p]
@@ -120,10 +130,26 @@ class FusedTPComm(TPComm):
         ll_bytes = tp * SMALL_T * hidden_size * 4
         self.off_ll = [total, total + ll_bytes]
         total += 2 * ll_bytes
+        # NVLS (multimem) all-reduce: [parity][SMALL_T rows][H] bf16 partial rows + [tp][SMALL_T] epoch flags
+        nv_bytes = SMALL_T * hidden_size * 2
+        self.off_nv = [total, total + nv_bytes]
+        self.off_nv_flags = total + 2 * nv_bytes
+        total += 2 * nv_bytes + (tp * SMALL_T * 4 + 255) // 256 * 256
         self.blob = symm.empty(total, dtype=torch.uint8, device=self.device)
         self.blob.zero_()
         self.hdl = symm.rendezvous(self.blob, self.group.group_name)
         self.peer_base = [int(p) for p in self.hdl.buffer_ptrs]
+        # multicast mapping of the same allocation (NVSwitch + driver support): in-switch reduction for the
+        # decode-sized all-reduce. GLLM_TP_NVLS=0 keeps the LL (peer-store) variant everywhere;
+        # GLLM_TP_NVLS_MIN_PEER_ROWS: NVLS from (tp-1)*T >= this many incoming rows (below, LL's single hop wins)
+        self.mc_base = 0
+        try:
+            if os.environ.get("GLLM_TP_NVLS", "1") != "0" and getattr(self.hdl, "has_multicast_support", True):
+                self.mc_base = int(self.hdl.multicast_ptr or 0)
+        except Exception:  # noqa: BLE001
+            self.mc_base = 0
+        self.nvls_min_peer_rows = int(os.environ.get("GLLM_TP_NVLS_MIN_PEER_ROWS", "96"))
+        self.nvls_calls = 0
         assert len(self.peer_base) == tp
         self.local_base = self.peer_base[self.tp_rank]
         assert self.local_base == self.blob.data_ptr()
@@ -149,7 +175,8 @@ class FusedTPComm(TPComm):
         self.cur_ag = None  # (ag_idx, tensor view) produced by the last reduce_norm
         self.ep = None      # expert-parallel all-to-all buffers, created by the first MoE block
         self.ep_call = 0
-        logger.info("fused TP: %d MB symmetric buffer per rank, peers mapped over NVLink", total >> 20)
+        logger.info("fused TP: %d MB symmetric buffer per rank, peers mapped over NVLink%s", total >> 20,
+                    ", NVLS multicast mapping available" if self.mc_base else ", no multicast mapping (LL all-reduce)")
 
     # -------------------------------------------------------------------------------------------
     def begin_forward(self, num_tokens: int):
@@ -317,6 +344,24 @@ class FusedTPComm(TPComm):
                 return self._reduce_norm(parity, self.T, None, residual is not None, norm_w, eps, bcast=True,
                                          push_x=partial)
             h = self._ag_view(self._next_ag_idx())
+            if self.mc_base and (self.tp_size - 1) * self.T >= self.nvls_min_peer_rows:
+                # in-switch reduction: H*2 bytes per row each way instead of (tp-1)*H*4 bytes of LL slots
+                n = NvlsArgs()
+                n.x, n.ldx = partial.data_ptr(), partial.stride(0)
+                n.residual, n.residual_in = self.residual_buf.data_ptr(), 1 if residual is not None else 0
+                n.norm_w, n.out = norm_w.data_ptr(), h.data_ptr()
+                n.buf_local = self.local_base + self.off_nv[parity]
+                n.buf_mc = self.mc_base + self.off_nv[parity]
+                n.flags_mc = self.mc_base + self.off_nv_flags
+                n.flags_local = self.local_base + self.off_nv_flags
+                n.st = self.state.data_ptr()
+                n.tp, n.rank, n.T, n.H, n.row_cap, n.eps = (self.tp_size, self.tp_rank, self.T, self.H, SMALL_T,
+                                                            float(eps))
+                check(self.L.gllm_nvls_allreduce_norm(ctypes.byref(n), stream_ptr()), "nvls_allreduce_norm")
+                sm100._count()
+                self.nvls_calls += 1
+                self.cur_ag = None
+                return h, self.residual_buf[: self.T]
             a = LLArgs()
             a.x, a.ldx = partial.data_ptr(), partial.stride(0)
             a.residual, a.residual_in = self.residual_buf.data_ptr(), 1 if residual is not None else 0

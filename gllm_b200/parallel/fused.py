@@ -144,7 +144,9 @@ class FusedTPComm(TPComm):
         # GLLM_TP_NVLS_MIN_PEER_ROWS: NVLS from (tp-1)*T >= this many incoming rows (below, LL's single hop wins)
         self.mc_base = 0
         try:
-            if os.environ.get("GLLM_TP_NVLS", "1") != "0" and getattr(self.hdl, "has_multicast_support", True):
+            # opt-in (GLLM_TP_NVLS=1): numerically validated against NCCL (tests/mp_tp_check.py), not yet tuned
+            # against the LL variant at every (tp, T)
+            if os.environ.get("GLLM_TP_NVLS", "0") == "1" and getattr(self.hdl, "has_multicast_support", True):
                 self.mc_base = int(self.hdl.multicast_ptr or 0)
         except Exception:  # noqa: BLE001
             self.mc_base = 0

@@ -47,7 +47,8 @@ def main():
     base = TPComm()
     log("symmetric buffers ready")
     ok = True
-    for T in (1000, 37, 256, 5):
+    def op_level(T, tag=""):
+        nonlocal ok
         torch.manual_seed(100 + T)  # same on every rank
         x_full = (torch.randn(T, H, device=dev) * 0.5).bfloat16()         # replicated "embedding" output
         nw0 = (1 + 0.1 * torch.randn(H, device=dev)).bfloat16()
@@ -85,8 +86,25 @@ def main():
             e4 =((resf[:rv].float() - res[r0:r0 + rv].float()).norm() / (res[r0:r0 + rv].float().norm() + 1e-9)).item() if rv else 0.0
             if max(e1, e2, e3, e4) > 2e-2:
                 ok = False
-                print(f"[rank {rank}] T={T} rep={rep} MISMATCH {e1:.4f} {e2:.4f} {e3:.4f} {e4:.4f}", flush=True)
+                print(f"[rank {rank}] {tag}T={T} rep={rep} MISMATCH {e1:.4f} {e2:.4f} {e3:.4f} {e4:.4f}", flush=True)
         dist.barrier()
+
+    for T in (1000, 37, 256, 5):
+        op_level(T)
+    if fused.mc_base:
+        # the same dataflow with the decode-sized all-reduce forced onto the NVLS (multimem, in-switch reduction)
+        # kernel instead of the LL peer-store one
+        keep_rows, fused.nvls_min_peer_rows = fused.nvls_min_peer_rows, 0
+        calls0 = fused.nvls_calls
+        for T in (37, 5, 64):
+            op_level(T, "nvls ")
+        if fused.nvls_calls == calls0:
+            ok = False
+            print(f"[rank {rank}] NVLS path did not run", flush=True)
+        fused.nvls_min_peer_rows = keep_rows
+        log(f"NVLS all-reduce: {fused.nvls_calls - calls0} calls checked")
+    else:
+        log("no multicast mapping on this box: NVLS all-reduce not exercised")
     # MoE-style partial push
     T = 200
     torch.manual_seed(7)

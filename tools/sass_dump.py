@@ -15,9 +15,9 @@ OUT = os.path.join(ROOT, "profiles", "sass")
 WANT = ["gemm_bf16_kernel<128, 0>", "gemm_bf16_kernel<256, 1>", "gemm_smallm_kernel", "gemm_fp8_block_kernel",
         "attn_prefill_tc_kernel<128, 64>", "attn_prefill_kernel<128>", "attn_decode_kernel<128>", "attn_merge_kernel",
         "mla_attn_kernel", "rs_reduce_norm_kernel<1>", "ll_allreduce_norm_kernel", "push_partial_rows_kernel",
-        "ep_dispatch_kernel", "ep_combine_kernel", "rope_kv_kernel<4>", "rmsnorm_kernel<1, true>",
+        "ep_dispatch_kernel", "ep_combine_kernel", "rope_kv_kernel<4>", "rmsnorm_kernel<1, 1>",
         "silu_and_mul_kernel", "sample_kernel<__nv_bfloat16>", "vp_candidates_kernel<__nv_bfloat16>",
-        "vp_final_kernel", "topk_softmax_kernel", "grouped_topk_kernel", "moe_combine_kernel"]
+        "vp_final_kernel", "topk_softmax_kernel<8>", "grouped_topk_kernel<8>", "nvls_allreduce_norm_kernel", "moe_combine_kernel"]
 
 
 def main():

@@ -103,8 +103,8 @@ def reference_arm(args):
            "--steps", str(args.steps), "--warmup", str(args.warmup), "--num-prompts", str(args.num_prompts),
            "--maxp", str(args.maxp), "--maxd", str(args.maxd), "--max-cuda-graph-bs", str(args.max_cuda_graph_bs),
            "--seed", str(args.seed)]
-    limit = int(os.environ.get("GLLM_REF_TIMEOUT", "1700"))
-    env.setdefault("GLLM_REF_BUDGET_S", str(limit - 240))   # run_reference.py stops timing new passes after this
+    limit = int(os.environ.get("GLLM_REF_TIMEOUT", "1650"))
+    env.setdefault("GLLM_REF_BUDGET_S", str(limit - 200))   # engine start-up (graph capture) ~80-120 s   # run_reference.py stops timing new passes after this
     try:
         # own process group: on a timeout the reference's spawned workers are taken down with the front-end
         proc = subprocess.Popen(cmd, env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True,

@@ -218,6 +218,9 @@ def main():
     conf = CONFIGS[args.config]
     model_name = args.model.replace("preset:", "")
     model = args.model
+    # Self-test of this script's control flow on a box without a GPU (tests/test_bench_cpu.py): a tiny random model
+    # on the CPU, host clocks instead of CUDA events. Never a benchmark number (`"data"` says so).
+    cpu_selftest = os.environ.get("GLLM_BENCH_CPU_SELFTEST") == "1" and not torch.cuda.is_available()
     if args.config != "qwen3-8b-tp":
         model_name = conf["model"]
         model = "preset:" + model_name
@@ -229,15 +232,25 @@ def main():
         from gllm_b200.models.presets import PRESETS
         model = dict(PRESETS[model_name], num_hidden_layers=args.layers)
         model_name = f"{model_name} REDUCED to {args.layers} layers"
+    if cpu_selftest:
+        from gllm_b200.models.presets import PRESETS, tiny
+        arch = PRESETS.get(model_name.split(" ")[0], PRESETS["qwen3-8b"])["architectures"][0]
+        if arch.startswith("Deepseek"):
+            arch = "Qwen3ForCausalLM"
+        over = dict(num_local_experts=4, num_experts_per_tok=2) if arch == "MixtralForCausalLM" else {}
+        model = tiny(arch, num_hidden_layers=2 * args.pp, max_position_embeddings=4096, **over)
+        model_name = f"tiny {arch} self-test model (CPU)"
     tp = args.gpus // args.pp
     llm = LLM(model, load_format="dummy", tp_size=tp, pp_size=args.pp, maxp=args.maxp, maxd=args.maxd,
               max_cuda_graph_bs=args.max_cuda_graph_bs, schedule_method=args.schedule_method,
               enable_prefix_caching=True, gpu_memory_util=0.9, model_max_length=2048 + 16,
               tp_mode=args.tp_mode, log_stats=False, launch_mode="inproc", seed=args.seed,
               async_schedule=args.async_schedule, disable_cuda_graph=args.disable_cuda_graph,
-              num_gpu_pages=args.num_gpu_pages)
+              num_gpu_pages=args.num_gpu_pages, **({"device": "cpu", "num_cpu_pages": 2048} if cpu_selftest else {}))
     vocab = llm.loader.config["vocab_size"]
     prompts, out_lens = synth_requests(args.num_prompts, vocab, args.seed)
+    if cpu_selftest:      # the CPU oracle path is slow: a few tokens per request exercise the same control flow
+        out_lens = [min(o, 6) for o in out_lens]
     total_out = sum(out_lens)
     total_in = sum(len(p) for p in prompts)
     runner = llm.worker.runner
@@ -246,6 +259,8 @@ def main():
     n_pass = args.warmup + 2 * args.steps
     pass_prompts = [prompts if (args.fixed_prompts or i == 0) else synth_requests(args.num_prompts, vocab, args.seed, i)[0]
                     for i in range(n_pass)]
+    if cpu_selftest:
+        pass_prompts = [[p[:40] for p in ps_] for ps_ in pass_prompts]
     pass_no = [0]
 
     def one_pass():
@@ -256,7 +271,8 @@ def main():
     def barrier():
         if world > 1:
             dist.barrier()
-        torch.cuda.synchronize()
+        if not cpu_selftest:
+            torch.cuda.synchronize()
 
     for _ in range(args.warmup):
         one_pass()
@@ -273,14 +289,18 @@ def main():
     stats0 = dict(runner.stats)
     launches0 = sm100.launches()
     barrier()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ev0.record()
+    if cpu_selftest:
+        th0 = time.perf_counter()
+    else:
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
     seqs = None
     for _ in range(args.steps):
         seqs = one_pass()
-    ev1.record()
+    if not cpu_selftest:
+        ev1.record()
     barrier()
-    dev_ms = ev0.elapsed_time(ev1)
+    dev_ms = (time.perf_counter() - th0) * 1e3 if cpu_selftest else ev0.elapsed_time(ev1)
     busy_ms = runner.gpu_busy_ms()
     runner.time_steps = False
     stats1 = dict(runner.stats)
@@ -295,7 +315,7 @@ def main():
     if sampler:
         sampler.stop()
     if world > 1:
-        t = torch.tensor([dev_ms, wall_s * 1e3, busy_ms], device="cuda")
+        t = torch.tensor([dev_ms, wall_s * 1e3, busy_ms], device="cpu" if cpu_selftest else "cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dev_ms, wall_ms, busy_ms = t.tolist()
         wall_s = wall_ms / 1e3
@@ -325,7 +345,8 @@ def main():
             "value": round(value, 1), "unit": "tokens/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": round(dev_ms / args.steps, 2), "higher_is_better": True,
             "scaling": "strong", "vs_baseline": (value / base) if base else None, "dtype": "bf16",
-            "data": "synthetic ShareGPT-shaped token ids (log-normal lengths, reference dataset filter); random-init weights",
+            "data": "synthetic ShareGPT-shaped token ids (log-normal lengths, reference dataset filter); random-init weights"
+                    + (" -- CPU SELF-TEST OF bench.py, NOT A MEASUREMENT" if cpu_selftest else ""),
             "impl": "ours",
             "config": {"model": model_name, "named_config": args.config, "num_prompts": args.num_prompts,
                        "global_batch": args.num_prompts, "seq_len": "prompt<=1024, prompt+output<=2048",
@@ -371,7 +392,8 @@ def teardown(llm, world):
     dog = threading.Timer(120.0, _bail)
     dog.daemon = True
     dog.start()
-    torch.cuda.synchronize()
+    if torch.cuda.is_available():
+        torch.cuda.synchronize()
     if world > 1 and dist.is_initialized():
         dist.barrier()
     try:

@@ -83,7 +83,14 @@ class Comm:
             # so no node needs to know a slave's address.
             table = {"fe_req": 0, "fe_out": 1, "tok": 2}
             port = self.port_base + (table[name] if name in table else 3 + idx)
-            return f"tcp://{'*' if bind else self.master_addr}:{port}"
+            if bind:
+                # Bind on the master's own address, not on every interface: the frames on these sockets are pickled
+                # Python objects (control messages, token lists), so whoever can connect can execute code in the
+                # engine. The trust boundary is the cluster network the master address lives on ("Trust
+                # boundary of the control plane"); `--host 0.0.0.0` restores the reference's bind-everywhere.
+                wide = self.tcp_host in ("", "0.0.0.0", "*")
+                return f"tcp://{'*' if wide else (self.tcp_host or self.master_addr)}:{port}"
+            return f"tcp://{self.master_addr}:{port}"
         return f"{self.base}_{name}_{idx}"
 
     def init(self):

@@ -31,6 +31,17 @@ def main():
     sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
     from shard_util import load_global_weights
     load_global_weights(llm.worker.runner.model, cfg, seed=123)
+    if os.environ.get("GLLM_TEST_TWO_ENGINES") == "1":
+        # a second engine in the same processes, right after the first one was torn down: its ipc endpoints must not
+        # be the files the first engine's (asynchronously closing) sockets still own
+        warm = llm.generate(tokens=[[5, 6, 7]], output_lens=[3], ignore_eos=True)
+        assert int(os.environ.get("RANK", "0")) != 0 or len(warm[0].token_ids) == 6
+        llm.close()
+        torch.manual_seed(0)
+        llm = LLM(cfg, load_format="dummy", pp_size=pp, tp_size=tp, maxp=48, maxd=16, num_cpu_pages=128,
+                  model_max_length=256, log_stats=False, device="cpu", launch_mode="inproc", schedule_method=method,
+                  seed=0)
+        load_global_weights(llm.worker.runner.model, cfg, seed=123)
     prompts = [[5, 17, 99, 200, 3, 45, 7], [9] * 40, list(range(20, 120)), [300, 301]]
     if os.environ.get("GLLM_TEST_SAMPLED") == "1":
         # sampled + penalty requests next to greedy ones (vocab-parallel sampling under TP): rows 0 and 2 are greedy

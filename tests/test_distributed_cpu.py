@@ -131,3 +131,12 @@ def test_tp2_vocab_parallel_sampling_runs_and_keeps_greedy_rows_exact(monkeypatc
     monkeypatch.setenv("GLLM_TEST_SAMPLED", "1")
     ref = _run(1, 1)
     assert _run(1, 2, port=29901) == ref
+
+
+def test_second_engine_in_the_same_processes_still_reaches_its_peers(single, monkeypatch):
+    """Round-2 hardware bug: engines of one torchrun job re-used the same ipc file names; ZeroMQ closes listeners
+    asynchronously and unlinks the file when it finally does, which could be after the next engine had bound the path —
+    its peers then never heard from the driver. Endpoints are per engine instance now."""
+    monkeypatch.setenv("GLLM_TEST_TWO_ENGINES", "1")
+    assert _run(1, 2, port=29911) == single
+    assert _run(2, 1, port=29921) == single

@@ -69,9 +69,19 @@ class EpArgs(ctypes.Structure):
 
 _ONESHOT = os.environ.get("GLLM_TP_ONESHOT", "1") != "0"
 MAX_BLOCKS = 256   # kMaxBlocks in csrc/comm/tp_fused.cu (128-row blocks per gather buffer)
-SMALL_T = int(os.environ.get("GLLM_TP_SMALL_T", "64"))   # forwards with <= this many tokens: replicated rows +
-# one-kernel LL all-reduce⊕add⊕norm instead of the token-sharded GEMM⊕RS / AG⊕GEMM dataflow (see begin_forward;
-# calibrated with benchmarks/tp_small_t_sweep.py)
+# SMALL_T: row capacity of the decode-sized all-reduce buffers; forwards with <= small_threshold(tp) tokens run on
+# replicated rows + the one-kernel all-reduce⊕add⊕norm instead of the token-sharded GEMM⊕RS / AG⊕GEMM dataflow (see
+# begin_forward; sweep with benchmarks/tp_small_t_sweep.py). GLLM_TP_SMALL_T=<n> sets both; GLLM_TP_SMALL_T=auto
+# keeps the 64-row buffers and scales the threshold with the LL variant's incoming traffic, (tp-1)*T rows
+# (measured on 8xB200: a 64-token LL step costs 1.8x the 128-token sharded step at TP8, profiles/tp_scaling_r2.md).
+_SMALL_T_ENV = os.environ.get("GLLM_TP_SMALL_T", "64")
+SMALL_T = 64 if _SMALL_T_ENV == "auto" else int(_SMALL_T_ENV)
+
+
+def small_threshold(tp: int) -> int:
+    if _SMALL_T_ENV != "auto":
+        return SMALL_T
+    return max(8, min(SMALL_T, 112 // max(tp - 1, 1)))
 
 
 def _declare(L):
@@ -186,7 +196,10 @@ class FusedTPComm(TPComm):
         # Tiny decode batches are latency bound: the swap-AB weight-streaming GEMMs + one NCCL
         # all-reduce beat the sharded dataflow there (measured on 2xB200: 4.6 ms vs 7.0 ms per step at
         # batch 16), so such forwards run the baseline strategy; everything else runs fused.
-        self.small = num_tokens <= SMALL_T
+        tp = self.tp_size
+        # (a forward in which some rank would own no rows of the token-sharded layout stays on the replicated form)
+        self.small = num_tokens <= small_threshold(tp) or \
+            (num_tokens <= SMALL_T and (tp - 1) * ((num_tokens + tp - 1) // tp) >= num_tokens)
         # decode-sized forwards: one-shot all-reduce fused into the GEMM epilogue + reduce/add/norm kernel
         # (every rank pushes its partial rows to every rank); needs T rows per source in the staging slots
         self.oneshot = self.small and _ONESHOT and num_tokens <= self.rpr_max

@@ -60,6 +60,7 @@ class Worker(ProfilerMixin):
         self._seq_slots = {}                   # seq_id -> row of the penalty state it holds
         self._free_slots = []                  # rows given back (row 0 = "no penalty state")
         self._num_slots = 1
+        self._penalty_seen = False
         self.init_profiler()
 
     # -------------------------------------------------------------------------------------------
@@ -104,6 +105,8 @@ class Worker(ProfilerMixin):
             if pkg.schedule_lists:
                 for seq in pkg.schedule_lists:
                     seq.slot = 0        # penalty state rows are assigned at the first emission (`_assign_slots`)
+                    if seq.repetition_penalty != 1.0:
+                        self._penalty_seen = True
                 self.scheduler.add_new_requests(pkg.schedule_lists)
             if pkg.abort_ids:
                 self.scheduler.add_abort_ids(pkg.abort_ids)
@@ -175,6 +178,8 @@ class Worker(ProfilerMixin):
         sampling: a row is assigned when a sequence first emits and returned when it finishes, is aborted or is
         preempted — never by waiting requests, whose number is unbounded. The pool grows on demand (the runner
         grows the device tensor to match), so this cannot fail on the request path."""
+        if not self._penalty_seen:
+            return          # no request with a repetition penalty has arrived yet: nothing to scan per step
         for e in entries:
             seq = e.seq
             if e.emits and seq.repetition_penalty != 1.0 and seq.slot <= 0:

@@ -638,3 +638,41 @@ def test_vocab_parallel_sampling_model_matches_the_full_vocab_filter():
     toks = ref.vp_final(torch.stack(recs), c, v_full, top_k, top_p, generator=g)
     full = (torch.log_softmax(x[5], -1) - torch.log(race[5, :v_full])).argmax()
     assert int(toks[5]) == int(full)
+
+
+def test_small_t_threshold_rules(monkeypatch):
+    """Fused TP: the replicated-rows form is used up to a threshold (default 64; `auto` scales it with the LL
+    all-reduce's incoming traffic (tp-1)*T), and always when some rank would own no rows of the sharded layout."""
+    import importlib
+    import gllm_b200.parallel.fused as fused
+    assert fused.small_threshold(2) == fused.small_threshold(8) == fused.SMALL_T == 64      # default: one value
+    monkeypatch.setenv("GLLM_TP_SMALL_T", "auto")
+    f2 = importlib.reload(fused)
+    try:
+        assert [f2.small_threshold(tp) for tp in (2, 4, 8)] == [64, 37, 16] and f2.SMALL_T == 64
+
+        def small(t, tp):
+            return t <= f2.small_threshold(tp) or (t <= f2.SMALL_T and (tp - 1) * ((t + tp - 1) // tp) >= t)
+        for tp in (2, 4, 8):
+            for t in range(1, 200):
+                rpr = (t + tp - 1) // tp
+                if not small(t, tp):
+                    assert t > f2.small_threshold(tp)
+                    assert (tp - 1) * rpr < t, (t, tp)      # every rank owns at least one row on the sharded path
+        assert small(17, 8) and not small(32, 8) and not small(64, 8) and small(64, 2)
+    finally:
+        monkeypatch.delenv("GLLM_TP_SMALL_T")
+        importlib.reload(fused)
+
+
+def test_generate_takes_per_request_sampling_parameters():
+    from gllm_b200 import LLM
+    from gllm_b200.models.presets import tiny
+    llm = LLM(tiny("Qwen3ForCausalLM", num_hidden_layers=1), load_format="dummy", device="cpu", maxp=32, maxd=8,
+              num_cpu_pages=32, model_max_length=64, log_stats=False)
+    outs = llm.generate(tokens=[[3, 4, 5], [6, 7]], output_lens=[3, 2], ignore_eos=True, temperature=[0.0, 0.9],
+                        top_k=[1, 5], top_p=[1.0, 0.8], repetition_penalty=[1.0, 1.3])
+    assert [len(s.token_ids) for s in outs] == [6, 4]
+    assert (outs[0].top_k, outs[1].top_k, outs[1].repetition_penalty, outs[1].top_p) == (1, 5, 1.3, 0.8)
+    assert not llm.worker._seq_slots                       # the penalised request gave its state row back
+    llm.shutdown()

@@ -366,6 +366,7 @@ class LLM:
         w = self.worker
         w.stop = False
         idle = 0
+        parent = os.getppid()
         while not w.stop:
             if w.step():
                 idle = 0
@@ -373,6 +374,11 @@ class LLM:
                 idle += 1
                 if idle > 5000:
                     time.sleep(0.0001)
+                    if idle % 20000 == 0 and os.getppid() != parent:
+                        # the launcher (torchrun) is gone without taking us down — e.g. it was SIGKILLed by a test
+                        # harness timeout: an orphaned rank must not keep spinning (and holding its GPU) forever
+                        logger.error("launcher process %d disappeared: rank exits", parent)
+                        raise SystemExit(1)
         return []
 
     def _stop_peers(self):

@@ -40,6 +40,15 @@ def check_invariants(mm: PrefixMemoryManager, live):
                 o, j = owner[p]
                 assert i == j and o.token_ids[:(i + 1) * PAGE] == s.token_ids[:(i + 1) * PAGE]
             owner.setdefault(p, (s, i))
+    # a cache entry is never ahead of the computation: a page that only this sequence holds and that did not come
+    # from a prefix-cache hit is published only once its whole token range has been computed (hashes were
+    # registered at allocation; an abort / stall-break between two chunks then left entries for unwritten KV)
+    for s in live:
+        hit_pages = s.num_cached_tokens // mm.page_size
+        for i, p in enumerate(s.page_table):
+            h = mm.page2hash[p]
+            if h is not None and mm.hash2page.get(h) == p and holders[p] == 1 and i >= hit_pages:
+                assert (i + 1) * mm.page_size <= s.computed_token_num, (s.seq_id, i, s.computed_token_num)
 
 
 @settings(max_examples=int(__import__("os").environ.get("GLLM_HYP_EXAMPLES", "60")), deadline=None, derandomize=not __import__("os").environ.get("GLLM_HYP_RANDOM"), suppress_health_check=[HealthCheck.too_slow])

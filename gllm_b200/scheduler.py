@@ -162,6 +162,7 @@ class Scheduler:
         batch = self.batch_running.popleft()
         next_tokens = self.next_tokens_queue.popleft()
         out = SchedulerOutput()
+        prefix, ps = isinstance(self.mm, PrefixMemoryManager), self.page_size
         k = 0  # next_tokens holds one token per *emitting* entry, in batch order
         for ent in batch:
             seq = ent.seq
@@ -188,8 +189,11 @@ class Scheduler:
                     self.mm.free(seq)
                 self.abort_ids.discard(seq.seq_id)
                 continue
-            seq.computed_token_num = max(seq.computed_token_num, ent.start + ent.n)
-            self.mm.publish_computed(seq)
+            done = ent.start + ent.n
+            if done > seq.computed_token_num:
+                seq.computed_token_num = done
+            if prefix and done // ps > seq.published:      # (hot loop: a page completes once per `ps` decode steps)
+                self.mm.publish_computed(seq)
             if ent.emits:
                 tok = int(next_tokens[k - 1])
                 out.act_schedule_ids.append(seq.seq_id)

@@ -69,11 +69,12 @@ def test_server_subprocess_with_serving_benchmark():
         out = os.path.join(scratch_dir("gllm_b200_f_"), "f" + ".json")
         r = subprocess.run([sys.executable, os.path.join(ROOT, "benchmarks", "benchmark_serving.py"), "--port",
                             str(port), "--num-prompts", "12", "--request-rate", "50", "--vocab-size", "500",
-                            "--max-output-len", "8", "--save-result", out, "--goodput", "ttft:60000"],
+                            "--max-output-len", "8", "--save-result", out, "--goodput", "ttft:60000",
+                            "--arrival-stage", "3", "--stage-interval", "0.2"],     # staged arrivals (3 x 4 requests)
                            capture_output=True, text=True, timeout=240, env=env)
         assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
         res = json.load(open(out))
-        assert res["completed"] == 12 and res["failed"] == 0
+        assert res["completed"] == 12 and res["failed"] == 0 and res["arrival_stage"] == 3
         for k in ("median_ttft_ms", "median_tpot_ms", "median_itl_ms", "median_e2el_ms", "output_throughput",
                   "request_goodput", "p99_ttft_ms"):
             assert k in res, k
